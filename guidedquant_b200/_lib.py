@@ -1,0 +1,101 @@
+"""Loader/builder of the C-ABI library libapgemv_b200.so (include/apgemv_b200.h).
+
+The library is built IN-TREE with nvcc for sm_100a only (guidedquant_b200/lib/), so it travels with
+the working tree.  There is no fallback: if the library cannot be built or loaded every entry point
+of this package raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_PKG)
+_CSRC = os.path.join(_PKG, "csrc")
+_LIBDIR = os.path.join(_PKG, "lib")
+LIB_PATH = os.path.join(_LIBDIR, "libapgemv_b200.so")
+_SOURCES = ["apgemv_capi.cu", "decode_capi.cu"]
+_HEADERS = ["apgemv_common.cuh", "apgemv_fast.cuh", "apgemv_generic.cuh", "decode_kernels.cuh"]
+
+NVCC_FLAGS = [
+    "-O3", "-std=c++17", "-lineinfo", "-shared", "-Xcompiler", "-fPIC",
+    "-gencode", "arch=compute_100a,code=sm_100a",
+]
+
+EXPORTS = (
+    "apg_version", "apg_status_string", "apg_last_cuda_error", "apg_gemv", "apg_gemv_ex", "apg_dequant",
+    "apg_round_f32_to_f16",
+)
+
+
+def _stale() -> bool:
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    deps = [os.path.join(_CSRC, f) for f in _SOURCES + _HEADERS] + [os.path.join(_ROOT, "include", "apgemv_b200.h")]
+    return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """nvcc -gencode arch=compute_100a,code=sm_100a ... -> guidedquant_b200/lib/libapgemv_b200.so"""
+    if not force and not _stale():
+        return LIB_PATH
+    os.makedirs(_LIBDIR, exist_ok=True)
+    srcs = [os.path.join(_CSRC, f) for f in _SOURCES if os.path.exists(os.path.join(_CSRC, f))]
+    cmd = ["nvcc", *NVCC_FLAGS, "-I" + os.path.join(_ROOT, "include"), "-I" + _CSRC, "-o", LIB_PATH, *srcs]
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed building libapgemv_b200.so:\n" + res.stdout + res.stderr)
+    if verbose:
+        print(res.stderr)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib() -> ctypes.CDLL:
+    """ctypes handle with typed signatures.  Raises (never falls back) if the library is unavailable."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        try:
+            build()
+        except Exception as e:  # no nvcc on this box and no prebuilt library
+            raise RuntimeError(
+                f"libapgemv_b200.so is missing ({LIB_PATH}) and could not be built: {e}. "
+                "Run `python -c 'import __graft_entry__ as g; g.build()'` where nvcc is available."
+            ) from e
+    L = ctypes.CDLL(LIB_PATH)
+    vp, u32, i32 = ctypes.c_void_p, ctypes.c_uint32, ctypes.c_int
+    L.apg_version.restype = i32
+    L.apg_status_string.restype = ctypes.c_char_p
+    L.apg_status_string.argtypes = [i32]
+    L.apg_last_cuda_error.restype = i32
+    L.apg_gemv.restype = i32
+    L.apg_gemv.argtypes = [vp, vp, vp, vp, u32, u32, u32, i32, vp]
+    L.apg_gemv_ex.restype = i32
+    L.apg_gemv_ex.argtypes = [vp, vp, vp, vp, vp, u32, u32, u32, i32, u32, i32, vp]
+    L.apg_dequant.restype = i32
+    L.apg_dequant.argtypes = [vp, vp, vp, u32, u32, i32, vp]
+    L.apg_round_f32_to_f16.restype = i32
+    L.apg_round_f32_to_f16.argtypes = [vp, vp, u32, vp]
+    _lib = L
+    return L
+
+
+def check(status: int, what: str) -> None:
+    if status != 0:
+        L = lib()
+        msg = L.apg_status_string(status).decode()
+        extra = f" (cudaError {L.apg_last_cuda_error()})" if status == 6 else ""
+        raise RuntimeError(f"{what}: {msg}{extra}")
+
+
+APG_FLAG_REF_ORDER = 0x1
+APG_FLAG_GENERIC = 0x2
+APG_FLAG_PDL = 0x4

@@ -1,0 +1,94 @@
+/*
+ * apgemv_b200 — C-ABI of the B200-native Any-Precision LUT GEMV (sm_100a).
+ *
+ * This header is the drop-in boundary for the reference's native extension `ap_gemv`
+ * (snu-mllab/GuidedQuant, inference/ap_gemv).  Each entry point names the reference interface
+ * it replaces; paths are relative to the reference root.  Plain pointers and sizes only: all
+ * pointers are DEVICE pointers on the current CUDA device, `stream` is a cudaStream_t / CUstream
+ * handle passed as void* (NULL = legacy default stream).  Every function returns 0 on success or
+ * one of the APG_ERR_* codes below; nothing here calls exit() or assert() (the reference does:
+ * inference/ap_gemv/gemv.cu:20-27, anyprec.cu:602).  Launches are asynchronous on `stream`
+ * and are CUDA-graph capturable; launch errors are reported (the reference does not check them,
+ * anyprec.cu:617-619).
+ *
+ * Tensor layouts (identical to the reference):
+ *   x        fp16 [M, K]            row-major (the reference's input [M,1,K], gemv.cu:41-43)
+ *   qweight  int32 [bits, N, K/32]  bit-plane major, MSB plane first, warp-permuted words
+ *                                   (any_precision/quantization/pack.py:12-83,304-321)
+ *   lut      fp16 [N, 2^bits]       per-output-row centroids
+ *   out      fp16 [M, N]            overwritten (anyprec.cu:538), never accumulated
+ */
+#ifndef APGEMV_B200_H
+#define APGEMV_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define APG_VERSION 100 /* major*100 + minor */
+
+enum apg_status {
+    APG_OK = 0,
+    APG_ERR_NULL = 1,     /* a required pointer is NULL */
+    APG_ERR_BITS = 2,     /* bits outside 2..8            (gemv.cu:64) */
+    APG_ERR_BATCH = 3,    /* M outside 1..8               (anyprec.cu:602) */
+    APG_ERR_SHAPE = 4,    /* K == 0, K % 32 != 0 or N == 0 (gemv.cu:76, APLinear.py:17) */
+    APG_ERR_ALIGN = 5,    /* a pointer is not aligned to its element/vector size */
+    APG_ERR_CUDA = 6,     /* the CUDA runtime reported an error; see apg_last_cuda_error() */
+    APG_ERR_MODE = 7,     /* unknown flag / mode / world layout */
+    APG_ERR_UNSUPPORTED = 8
+};
+
+/* flags for apg_gemv_ex */
+#define APG_FLAG_REF_ORDER 0x1u /* reproduce the reference kernel's fp16 accumulation order bit for
+                                   bit (matmul_kbit_32, anyprec.cu:424-541); slow, for parity tests */
+#define APG_FLAG_GENERIC 0x2u   /* force the generic (untuned) kernel */
+#define APG_FLAG_PDL 0x4u       /* launch with programmatic dependent launch: weight/LUT prefetch
+                                   overlaps the tail of the previous kernel on the stream */
+
+int apg_version(void);
+const char *apg_status_string(int status);
+/* cudaError_t of the last failing runtime call made by this library on the calling thread. */
+int apg_last_cuda_error(void);
+
+/*
+ * Replaces ap_gemv.anyprec_gemv(input, output, qweight, lut, bitwidth)
+ *   (inference/ap_gemv/gemv.cu:96-107 -> anyprec_matmul, anyprec.cu:591-620).
+ * out[m, n] = sum_k lut[n, idx[n, k]] * x[m, k]  for m < M (1..8), bits in 2..8.
+ * Requirements: K % 32 == 0 (layout), any N >= 1 (the reference silently drops rows when
+ * N % 4 != 0, anyprec.cu:614; this library computes them).
+ */
+int apg_gemv(const void *x, void *out, const void *qweight, const void *lut,
+             uint32_t M, uint32_t N, uint32_t K, int bits, void *stream);
+
+/*
+ * apg_gemv with options.
+ *   flags        APG_FLAG_*.
+ *   partial_f32  optional fp32 [M, N] output: if non-NULL the un-rounded fp32 sums are written
+ *                there as well (used by the K-sharded multi-GPU path, where partial sums are
+ *                all-reduced in fp32 and rounded once); `out` may then be NULL.
+ *   ctas_per_sm  0 = heuristic; otherwise forces the grid to ctas_per_sm * SM count (tuning).
+ */
+int apg_gemv_ex(const void *x, void *out, float *partial_f32, const void *qweight, const void *lut,
+                uint32_t M, uint32_t N, uint32_t K, int bits, uint32_t flags, int ctas_per_sm,
+                void *stream);
+
+/*
+ * Replaces ap_gemv.anyprec_dequant(qweight, lut, bitwidth) -> fp16 [N, K]
+ *   (inference/ap_gemv/gemv.cu:109-134 -> dequant_kbit_store, anyprec.cu:294-359, 622-645).
+ * w_out[n, k] = lut[n, idx[n, k]] — a pure gather, bit-identical to the reference.
+ * The caller allocates w_out (N*K fp16); the torch layer allocates it like the reference does.
+ */
+int apg_dequant(const void *qweight, const void *lut, void *w_out,
+                uint32_t N, uint32_t K, int bits, void *stream);
+
+/* fp32 [n] -> fp16 [n] round-to-nearest-even, optionally adding an fp16 bias; the epilogue of the
+ * K-sharded path after the fp32 all-reduce. */
+int apg_round_f32_to_f16(const float *in, void *out, uint32_t n, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* APGEMV_B200_H */

@@ -1,0 +1,185 @@
+"""GPU parity tests (run with -m gpu on the B200 box).  Everything goes through the C-ABI library
+(guidedquant_b200.ap_gemv -> libapgemv_b200.so); the CPU oracle (oracle/) and the compiled reference
+kernels (oracle/_ref) are the checkers.
+
+Bars:
+  * index unpack: dequant output bit-identical to the oracle AND to the reference kernel;
+  * APG_FLAG_REF_ORDER GEMV: bit-identical to the reference kernel and to the oracle's fp16 emulation;
+  * fast GEMV (fp32 cross-chain accumulation): max|y - y_f64| / max|y_f64| <= 5e-4 and
+    max|y - y_ref| / max|y_ref| <= 2.5e-3  (the reference's own all-fp16 accumulation sits 1.0-1.5e-3 from
+    the fp64 truth, SURVEY.md §7.3-2, so its noise floor bounds the second figure).
+"""
+import numpy as np
+import pytest
+import torch
+
+from tests import refgpu
+
+pytestmark = pytest.mark.gpu
+
+TOL_TRUTH = 5e-4
+TOL_REF = 2.5e-3
+
+
+def _t(a, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    return t.cuda() if dtype is None else t.to(dtype).cuda()
+
+
+def _nerr(y, ref):
+    y = np.asarray(y, dtype=np.float64).reshape(-1)
+    ref = np.asarray(ref, dtype=np.float64).reshape(-1)
+    return float(np.abs(y - ref).max() / max(np.abs(ref).max(), 1e-30))
+
+
+def _run(x, q, lut, bits, flags=0, ctas=0):
+    from guidedquant_b200 import ap_gemv
+
+    out = torch.full((x.shape[0], 1, q.shape[1]), float("nan"), dtype=torch.float16, device="cuda")
+    ap_gemv.anyprec_gemv_ex(x, out, q, lut, bits, flags=flags, ctas_per_sm=ctas)
+    torch.cuda.synchronize()
+    return out
+
+
+CASES_FAST = [  # (N, K, bits)  M = 1
+    (64, 4096, 2), (64, 4096, 3), (64, 4096, 4),
+    (100, 4096, 2), (7, 4096, 3), (5, 4096, 4), (1, 4096, 2),          # ragged N (no N % 4 requirement)
+    (48, 11008, 2), (48, 11008, 3), (48, 11008, 4),                   # tail chunk eff = 24 (Llama-2-7B w2)
+    (32, 13824, 2), (32, 14336, 2), (32, 14336, 3), (32, 14336, 4),   # multi-slab, eff = 16 / half slab
+    (32, 8192, 2), (16, 28672, 2), (16, 28672, 4), (24, 3584, 2),     # 70B shapes, 70B w2 shard 3584
+    (32, 128, 2), (32, 1152, 3), (32, 2048, 4), (40, 5120, 2),
+]
+
+
+@pytest.mark.parametrize("N,K,bits", CASES_FAST)
+def test_fast_gemv_vs_oracle(oracle, N, K, bits):
+    from guidedquant_b200._lib import APG_FLAG_GENERIC
+
+    idx, q, lut, x = oracle.synth_layer(N, K, bits, seed=N + K)
+    W = oracle.dequant(q, lut, bits)
+    y64 = oracle.gemv_f64(W, x)
+    yref = oracle.gemv_ref_order_f16(W, x)
+    xq, qq, ll = _t(x), _t(q), _t(lut)
+    for ctas in (0, 1, 3):
+        y = _run(xq, qq, ll, bits, ctas=ctas).cpu().numpy().reshape(1, N)
+        assert not np.isnan(y).any()
+        assert _nerr(y, y64) <= TOL_TRUTH, (N, K, bits, ctas, _nerr(y, y64))
+        assert _nerr(y, yref) <= TOL_REF
+    yg = _run(xq, qq, ll, bits, flags=APG_FLAG_GENERIC).cpu().numpy().reshape(1, N)
+    assert _nerr(yg, y64) <= TOL_TRUTH
+
+
+@pytest.mark.parametrize("N,K,bits,M", [(32, 4096, 2, 1), (32, 2048, 3, 2), (48, 11008, 4, 3), (16, 1024, 5, 1),
+                                         (16, 2080, 6, 4), (16, 1024, 7, 8), (16, 4096, 8, 1), (32, 96, 2, 5),
+                                         (16, 4096, 4, 8)])
+def test_ref_order_bit_exact_vs_oracle_and_generic(oracle, N, K, bits, M):
+    from guidedquant_b200._lib import APG_FLAG_GENERIC, APG_FLAG_REF_ORDER
+
+    idx, q, lut, x = oracle.synth_layer(N, K, bits, seed=3 * N + K + M, M=M)
+    W = oracle.dequant(q, lut, bits)
+    y_emul = oracle.gemv_ref_order_f16(W, x)
+    y64 = oracle.gemv_f64(W, x)
+    xq, qq, ll = _t(x), _t(q), _t(lut)
+    y = _run(xq, qq, ll, bits, flags=APG_FLAG_REF_ORDER).cpu().numpy().reshape(M, N)
+    assert np.array_equal(y.view(np.uint16), y_emul.view(np.uint16))
+    yg = _run(xq, qq, ll, bits, flags=APG_FLAG_GENERIC).cpu().numpy().reshape(M, N)
+    assert _nerr(yg, y64) <= TOL_TRUTH
+    y0 = _run(xq, qq, ll, bits).cpu().numpy().reshape(M, N)  # default dispatch (fast or generic)
+    assert _nerr(y0, y64) <= TOL_TRUTH
+
+
+@pytest.mark.parametrize("N,K,bits", [(64, 4096, 2), (64, 4096, 3), (64, 4096, 4), (16, 11008, 2), (16, 13824, 3),
+                                       (8, 96, 4), (12, 1024, 5), (8, 2048, 8), (7, 1056, 2)])
+def test_dequant_bit_exact(oracle, N, K, bits):
+    from guidedquant_b200 import ap_gemv
+
+    idx, q, lut, _ = oracle.synth_layer(N, K, bits, seed=N)
+    # hostile codebook values: +-65504, denormals, -0
+    lut = lut.copy()
+    lut[0, 0], lut[0, 1], lut[-1, -1], lut[-1, 0] = 65504.0, -65504.0, np.float16(6e-8), np.float16(-0.0)
+    W = ap_gemv.anyprec_dequant(_t(q), _t(lut), bits).cpu().numpy()
+    Wo = oracle.dequant(q, lut, bits)
+    assert W.shape == (N, K)
+    assert np.array_equal(W.view(np.uint16), Wo.view(np.uint16))
+    assert np.array_equal(W.view(np.uint16), lut.view(np.uint16)[np.arange(N)[:, None], idx])
+
+
+@pytest.mark.skipif(not refgpu.available(), reason="oracle/_ref/libapgemv_ref.so not built")
+@pytest.mark.parametrize("N,K,bits,M", [(64, 4096, 2, 1), (64, 4096, 3, 1), (64, 4096, 4, 1), (32, 11008, 2, 1),
+                                         (32, 14336, 2, 1), (32, 13824, 3, 1), (32, 28672, 2, 1), (32, 2048, 5, 1),
+                                         (32, 4096, 3, 4), (32, 4096, 4, 8), (32, 4096, 2, 2)])
+def test_against_compiled_reference_kernels(oracle, N, K, bits, M):
+    """The UNMODIFIED reference kernels (anyprec.cu compiled for sm_100a) on the same tensors."""
+    from guidedquant_b200 import ap_gemv
+    from guidedquant_b200._lib import APG_FLAG_REF_ORDER
+
+    idx, q, lut, x = oracle.synth_layer(N, K, bits, seed=11 * N + K, M=M)
+    xq, qq, ll = _t(x), _t(q), _t(lut)
+    y_ref = refgpu.ref_gemv(xq, qq, ll, bits)
+    w_ref = refgpu.ref_dequant(qq, ll, bits)
+    torch.cuda.synchronize()
+    # (1) dequant: bit-identical
+    w = ap_gemv.anyprec_dequant(qq, ll, bits)
+    assert torch.equal(w.view(torch.int16), w_ref.view(torch.int16))
+    # (2) reference-order mode: bit-identical to the reference kernel, and the oracle's emulation too
+    y_exact = _run(xq, qq, ll, bits, flags=APG_FLAG_REF_ORDER)
+    assert torch.equal(y_exact.view(torch.int16), y_ref.view(torch.int16))
+    W = oracle.dequant(q, lut, bits)
+    y_emul = oracle.gemv_ref_order_f16(W, x)
+    assert np.array_equal(y_ref.cpu().numpy().reshape(M, N).view(np.uint16), y_emul.view(np.uint16))
+    # (3) default path within the stated tolerance of the reference
+    y = _run(xq, qq, ll, bits)
+    assert _nerr(y.cpu().numpy(), y_ref.cpu().numpy()) <= TOL_REF
+
+
+def test_full_size_properties(oracle):
+    """BASELINE-size layer (4096x4096, 2-bit): size-independent properties instead of the slow oracle.
+    linearity in x, permutation of output rows, all-equal codebook -> y = c * sum(x)."""
+    from guidedquant_b200 import ap_gemv
+
+    N = K = 4096
+    g = torch.Generator(device="cuda").manual_seed(5)
+    q = torch.randint(-2**31, 2**31 - 1, (2, N, K // 32), dtype=torch.int32, device="cuda", generator=g)
+    lut = (torch.randn((N, 4), device="cuda", generator=g) * 0.02).half()
+    x1 = torch.randn((1, 1, K), device="cuda", generator=g).half()
+    y1 = _run(x1, q, lut, 2).float()
+    # linearity: y(2x) == 2 y(x) up to fp16-denormal effects inside the short fp16 chains
+    y2 = _run((x1 * 2).half(), q, lut, 2).float()
+    assert float((y2 - 2 * y1).abs().max() / (2 * y1).abs().max()) <= 1e-3
+    # dequant -> fp32 matmul (torch) agrees
+    W = ap_gemv.anyprec_dequant(q, lut, 2).float()
+    yt = (W @ x1.float().reshape(K, 1)).reshape(1, 1, N)
+    assert float((y1 - yt).abs().max() / yt.abs().max()) <= TOL_TRUTH
+    # row permutation of (qweight, lut) permutes y
+    perm = torch.randperm(N, device="cuda", generator=g)
+    yp = _run(x1, q[:, perm].contiguous(), lut[perm].contiguous(), 2).float()
+    assert torch.equal(yp, y1[..., perm])
+    # constant codebook: every weight equals c_n -> y_n = c_n * sum(x)
+    lut_c = lut[:, :1].repeat(1, 4).contiguous()
+    yc = _run(x1, q, lut_c, 2).float().reshape(N)
+    expect = lut_c[:, 0].float() * x1.float().sum()
+    assert float((yc - expect).abs().max() / expect.abs().max()) <= 2e-3
+
+
+def test_error_behaviour():
+    from guidedquant_b200 import ap_gemv
+
+    x = torch.zeros((1, 1, 128), dtype=torch.float16, device="cuda")
+    q = torch.zeros((2, 8, 4), dtype=torch.int32, device="cuda")
+    lut = torch.zeros((8, 4), dtype=torch.float16, device="cuda")
+    out = torch.zeros((1, 1, 8), dtype=torch.float16, device="cuda")
+    ap_gemv.anyprec_gemv(x, out, q, lut, 2)
+    with pytest.raises(RuntimeError, match="Bitwidth"):
+        ap_gemv.anyprec_gemv(x, out, q, lut, 9)
+    with pytest.raises(RuntimeError, match="lut tensor must be of shape"):
+        ap_gemv.anyprec_gemv(x, out, q, lut[:, :2].contiguous(), 2)
+    with pytest.raises(RuntimeError, match="qweight tensor must be of shape"):
+        ap_gemv.anyprec_gemv(x, out, q[:, :4].contiguous(), lut, 2)
+    with pytest.raises(RuntimeError, match="sequence length"):
+        ap_gemv.anyprec_gemv(x.reshape(1, 1, 128).expand(1, 2, 128).contiguous(), out, q, lut, 2)
+    with pytest.raises(RuntimeError, match="contiguous"):
+        ap_gemv.anyprec_gemv(x, out, q.transpose(1, 2).contiguous().transpose(1, 2), lut, 2)
+    with pytest.raises(RuntimeError, match="float16"):
+        ap_gemv.anyprec_gemv(x.bfloat16(), out.bfloat16(), q, lut.bfloat16(), 2)
+    with pytest.raises(RuntimeError, match="type int"):
+        ap_gemv.anyprec_gemv(x, out, q.long(), lut, 2)
