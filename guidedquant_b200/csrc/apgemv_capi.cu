@@ -25,7 +25,6 @@ inline int cuda_fail(cudaError_t e) {
 
 struct DevInfo {
     int sms = 0;
-    bool fast_attr_set[5] = {false, false, false, false, false};
 };
 DevInfo g_dev[64];
 
@@ -45,52 +44,63 @@ int device_info(DevInfo **out) {
 
 inline bool aligned(const void *p, uintptr_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
 
-constexpr size_t kFastMaxSmem = 100 * 1024;
+constexpr size_t kFastMaxSmem = 200 * 1024;
 
+struct FastPlan {
+    uint32_t cpw, nwk, groups, rs, nslots, stage_bytes, grid, rows_per_cta, threads;
+    size_t smem;
+};
+
+// Work decomposition of the fast kernel: consumer warps per CTA, rows per stage, ring depth, grid.
 template <int BITS>
-int launch_fast(const void *x, void *out, float *partial, const void *qweight, const void *lut, uint32_t N,
-                uint32_t K, uint32_t flags, int ctas_per_sm, cudaStream_t stream, DevInfo *dev) {
-    using namespace apg;
-    const uint32_t nslab = (K + 4095u) / 4096u;
-    const uint32_t groups = nslab >= 4 ? 1u : (4u / nslab);
-    const uint32_t warps = nslab * groups;
-    const size_t smem = fast_smem_bytes<BITS>(nslab, groups);
-    if (smem > kFastMaxSmem) return APG_ERR_UNSUPPORTED;
-    if (!dev->fast_attr_set[BITS]) {
-        APG_CUDA(cudaFuncSetAttribute(gemv_fast_kernel<BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)kFastMaxSmem));
-        dev->fast_attr_set[BITS] = true;
-    }
-    // grid: ctas_per_sm CTAs on every SM, one wave; rows are split evenly over all row groups.
-    int c = ctas_per_sm;
-    if (c <= 0) {
-        const uint32_t c_max = warps >= 8 ? 2u : (warps >= 6 ? 2u : (16u / warps));
-        const uint32_t target_rows = 2u * FastCfg<BITS>::RB;
-        uint32_t want = (N + dev->sms * groups * target_rows - 1) / (dev->sms * groups * target_rows);
-        if (want < 1) want = 1;
-        if (want > c_max) want = c_max;
-        c = (int)want;
-    }
-    uint32_t grid = (uint32_t)dev->sms * (uint32_t)c;
-    const uint32_t max_useful = (N + groups - 1) / groups;  // at least one row per group
-    if (grid > max_useful) grid = max_useful;
+bool plan_fast(uint32_t N, uint32_t K, int ctas_per_sm, int sms, FastPlan *pl) {
+    const uint32_t nchunk = (K + 1023u) / 1024u;
+    if (nchunk > 32) return false;
+    pl->cpw = nchunk > 16 ? 2u : 1u;
+    pl->nwk = (nchunk + pl->cpw - 1) / pl->cpw;                  // <= 16
+    pl->groups = pl->nwk >= 8 ? 1u : (8u / pl->nwk);              // ~8 consumer warps per CTA (up to 16)
+    const uint32_t ncons = pl->groups * pl->nwk;
+    pl->threads = (ncons + 1) * 32u;
+    const uint32_t row_bytes = K / 8u * BITS;                     // all planes of one row
+    uint32_t rs = 8;
+    while (rs > 2 && rs * row_bytes > 16u * 1024u) rs >>= 1;      // stage <= 16 KB where possible
+    pl->rs = rs;
+    pl->stage_bytes = rs * row_bytes;
+    int c = ctas_per_sm > 0 ? ctas_per_sm : (ncons <= 8 ? 2 : 1);
+    uint32_t grid = (uint32_t)sms * (uint32_t)c;
+    const uint32_t max_grid = (N + rs - 1) / rs;                  // at least one stage per CTA
+    if (grid > max_grid) grid = max_grid;
     if (grid < 1) grid = 1;
+    pl->grid = grid;
+    pl->rows_per_cta = (N + grid - 1) / grid + 1;
+    const uint32_t stages_per_cta = (pl->rows_per_cta + rs - 1) / rs;
+    // ring: as deep as the CTA's share needs, bounded so that c CTAs (+ a dependent kernel's) fit in 227 KB
+    const size_t ring_budget = (c >= 2 ? 56u : 96u) * 1024u;
+    uint32_t ns = (uint32_t)(ring_budget / pl->stage_bytes);
+    if (ns > stages_per_cta + pl->groups - 1) ns = stages_per_cta + pl->groups - 1;
+    ns = ns / pl->groups * pl->groups;
+    if (ns < pl->groups) ns = pl->groups;
+    pl->nslots = ns;
+    const uint32_t wtb = rs == 8 ? apg::FastWarpTbl<BITS, 8>::BYTES : (rs == 4 ? apg::FastWarpTbl<BITS, 4>::BYTES : apg::FastWarpTbl<BITS, 2>::BYTES);
+    pl->smem = 2 * (size_t)ns * 8 + 256 + (size_t)ncons * wtb + (size_t)ns * pl->stage_bytes +
+               (size_t)pl->rows_per_cta * pl->nwk * sizeof(float) + 16;
+    return pl->smem <= kFastMaxSmem;
+}
 
-    FastParams p;
-    p.x = static_cast<const __half *>(x);
-    p.W = static_cast<const uint4 *>(qweight);
-    p.lut = static_cast<const __half *>(lut);
-    p.out = static_cast<__half *>(out);
-    p.partial = partial;
-    p.N = N;
-    p.K = K;
-    p.nslab = nslab;
-    p.groups = groups;
-
+template <int BITS, int CPW, int RS>
+int launch_fast_inst(const apg::FastParams &p, const FastPlan &pl, uint32_t flags, cudaStream_t stream) {
+    static bool attr_set[64] = {false};
+    int dev = 0;
+    APG_CUDA(cudaGetDevice(&dev));
+    if (!attr_set[dev & 63]) {
+        APG_CUDA(cudaFuncSetAttribute(apg::gemv_fast_kernel<BITS, CPW, RS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)kFastMaxSmem));
+        attr_set[dev & 63] = true;
+    }
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(warps * 32u);
-    cfg.dynamicSmemBytes = smem;
+    cfg.gridDim = dim3(pl.grid);
+    cfg.blockDim = dim3(pl.threads);
+    cfg.dynamicSmemBytes = pl.smem;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     if (flags & APG_FLAG_PDL) {
@@ -99,8 +109,37 @@ int launch_fast(const void *x, void *out, float *partial, const void *qweight, c
         cfg.attrs = attr;
         cfg.numAttrs = 1;
     }
-    APG_CUDA(cudaLaunchKernelEx(&cfg, gemv_fast_kernel<BITS>, p));
+    APG_CUDA(cudaLaunchKernelEx(&cfg, apg::gemv_fast_kernel<BITS, CPW, RS>, p));
     return APG_OK;
+}
+
+template <int BITS>
+int launch_fast(const void *x, void *out, float *partial, const void *qweight, const void *lut, uint32_t N,
+                uint32_t K, uint32_t flags, int ctas_per_sm, cudaStream_t stream, DevInfo *dev) {
+    FastPlan pl;
+    if (!plan_fast<BITS>(N, K, ctas_per_sm, dev->sms, &pl)) return APG_ERR_UNSUPPORTED;
+    apg::FastParams p;
+    p.x = static_cast<const __half *>(x);
+    p.W = static_cast<const uint8_t *>(qweight);
+    p.lut = static_cast<const __half *>(lut);
+    p.out = static_cast<__half *>(out);
+    p.partial = partial;
+    p.N = N;
+    p.K = K;
+    p.nwk = pl.nwk;
+    p.groups = pl.groups;
+    p.nslots = pl.nslots;
+    p.stage_bytes = pl.stage_bytes;
+#define APG_FAST_CASE(CPW_, RS_) \
+    if (pl.cpw == CPW_ && pl.rs == RS_) return launch_fast_inst<BITS, CPW_, RS_>(p, pl, flags, stream);
+    APG_FAST_CASE(1, 8)
+    APG_FAST_CASE(1, 4)
+    APG_FAST_CASE(1, 2)
+    APG_FAST_CASE(2, 8)
+    APG_FAST_CASE(2, 4)
+    APG_FAST_CASE(2, 2)
+#undef APG_FAST_CASE
+    return APG_ERR_UNSUPPORTED;
 }
 
 }  // namespace

@@ -1,362 +1,504 @@
 // Fast Any-Precision LUT GEMV for M = 1, bits in {2,3,4}, K % 128 == 0, K <= 32768  (sm_100a).
 //
-// Replaces matmul_kbit_32<1,bits,false> (reference inference/ap_gemv/anyprec.cu:372-542) with a
-// different work decomposition:
-//   * 128-bit coalesced loads of the bit-planes: lane L of a warp owns words 4L..4L+3 of a
-//     128-word "slab" (4096 k) of a (row, plane) -> one LDG.128 per plane = 128 weights.
-//   * the lane<->k map is row-independent, so the lane's 128 activations live in
-//     64 half2 REGISTERS for the whole kernel (the reference re-reads x from L1/L2 for every row).
-//   * per-row codebooks are expanded once per row-batch into conflict-free shared-memory tables
-//     (<= 32 banks for 2/4-bit): 2-bit -> 16-entry pair table (one LDS = two weights),
-//     3-bit -> 64-entry pair table, 4-bit -> 16-entry scalar table.
-//   * table byte-offsets are produced four at a time (masked words) and turned into complete LDS
-//     addresses by ONE PRMT each (byte insert into a 256-byte-aligned per-warp table base).
-//   * fp16 HFMA2 chains of length 8 feed fp32 accumulators (the reference accumulates everything
-//     in fp16); rows are reduced RB at a time with a transposing shuffle tree.
-//   * K > 4096: the row's slabs are spread over the warps of a group (each warp keeps ITS slab's x
-//     in registers) and combined through shared memory.
+// Replaces matmul_kbit_32<1,bits,false> (reference inference/ap_gemv/anyprec.cu:372-542).  Same math,
+// same packed tensors, different machine mapping:
+//
+//   * WEIGHT STREAM: one producer thread per CTA streams the CTA's contiguous row range through a
+//     shared-memory ring with 1-D bulk async copies (cp.async.bulk -> UBLKCP, completion on mbarriers):
+//     a stage = RS rows x BITS planes x K/8 bytes.  No registers are spent on prefetch, the ring keeps
+//     tens of KB per SM in flight, and under programmatic dependent launch the ring fills while the
+//     previous kernel is still running (weights do not depend on it; only x does).
+//   * CONSUMER WARPS own one 1024-wide K chunk each (CPW = 2: two chunks): lane t owns word t of the
+//     chunk in every plane, i.e. k = i*1024 + c*8*eff + 8t + e (pack.py:58-75).  That map is
+//     row-independent, so the lane's 32 activations per chunk live in 16 half2 REGISTERS for the whole
+//     kernel (the reference re-reads x through L1 for every row); they are fetched with four fully
+//     coalesced LDG.128.
+//   * CODEBOOKS: each warp expands the stage's lut rows into conflict-free shared-memory tables
+//     (2-bit: 16-entry half2 pair table = 64 B, one LDS yields two weights; 3-bit: 64-entry pair table;
+//     4-bit: the 16 halfs as they are).  Table byte offsets are produced four at a time (masked words)
+//     and every lookup address is formed by ONE PRMT (byte insert into a 256-B aligned table base).
+//   * ARITHMETIC: fp16 HFMA2 chains of length 8 -> fp32 accumulators (the reference is fp16 end to
+//     end); RS rows are reduced together with a transposing shuffle tree (9 SHFL for 8 rows); the
+//     per-chunk partial sums meet in shared memory and are added in a fixed order (deterministic).
 #pragma once
 #include "apgemv_common.cuh"
 
 namespace apg {
 
+// ------------------------------------------------------------------------------------------------
+// mbarrier / bulk-copy primitives (PTX ISA: mbarrier, cp.async.bulk)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+// global -> shared 1-D bulk copy, completion (bytes) signalled on an mbarrier; L2 evict-first (streamed once)
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar, uint64_t pol) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+        "l"(src), "r"(bytes), "r"(bar), "l"(pol)
+        : "memory");
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-bit-width configuration
+// ------------------------------------------------------------------------------------------------
 template <int BITS>
 struct FastCfg;
 template <>
 struct FastCfg<2> {
-    static constexpr int RB = 4;              // rows per batch (8 LDG.128 in flight per lane)
     static constexpr int ROW_TBL_BYTES = 64;  // 16 x half2
 };
 template <>
 struct FastCfg<3> {
-    static constexpr int RB = 4;               // 12 LDG.128 in flight per lane
     static constexpr int ROW_TBL_BYTES = 256;  // 64 x half2
 };
 template <>
 struct FastCfg<4> {
-    static constexpr int RB = 2;              // 8 LDG.128 in flight per lane
     static constexpr int ROW_TBL_BYTES = 32;  // 16 x half
 };
-template <int BITS>
+template <int BITS, int RS>
 struct FastWarpTbl {
-    static constexpr int BYTES = (FastCfg<BITS>::RB * FastCfg<BITS>::ROW_TBL_BYTES + 255) / 256 * 256;
+    static constexpr int BYTES = (RS * FastCfg<BITS>::ROW_TBL_BYTES + 255) / 256 * 256;
 };
 
-// ---------------------------------------------------------------------------------------------
-// Codebook staging: expand lut rows [row0, row0+RB) into this warp's shared-memory tables.
-// ---------------------------------------------------------------------------------------------
-template <int BITS>
-__device__ __forceinline__ void stage_tables(uint32_t tbl_addr, const __half *__restrict__ lut, uint32_t row0,
-                                             uint32_t N, int lane);
-
-// 2-bit pair table: entry p = (hA hB lA lB) -> half2( C[2hA+lA], C[2hB+lB] ); A = even k (low half).
+// ------------------------------------------------------------------------------------------------
+// Transposing warp reduction over RS accumulators: afterwards lane (r << SH) holds row r's total.
+// ------------------------------------------------------------------------------------------------
+template <int RS>
+struct BatchReduce;
 template <>
-__device__ __forceinline__ void stage_tables<2>(uint32_t tbl_addr, const __half *__restrict__ lut, uint32_t row0,
-                                                uint32_t N, int lane) {
-    const int p = lane & 15;
-    const uint32_t a = ((p >> 3) & 1) * 2 + ((p >> 1) & 1), b = ((p >> 2) & 1) * 2 + (p & 1);
-    const uint32_t sel = (2 * a) | ((2 * a + 1) << 4) | ((2 * b) << 8) | ((2 * b + 1) << 12);
+struct BatchReduce<8> {
+    static constexpr int SH = 2;
+    __device__ __forceinline__ static float run(const float (&s)[8], int lane) {
+        const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+        float a[4];
 #pragma unroll
-    for (int it = 0; it < FastCfg<2>::RB / 2; it++) {
-        const int r = it * 2 + (lane >> 4);
-        const uint32_t row = min(row0 + r, N - 1);
-        const uint2 c = __ldg(reinterpret_cast<const uint2 *>(lut + (size_t)row * 4));
-        const uint32_t e = __byte_perm(c.x, c.y, sel);
-        asm volatile("st.shared.b32 [%0], %1;" ::"r"(tbl_addr + r * 64 + p * 4), "r"(e));
+        for (int i = 0; i < 4; i++) {
+            const float keep = b4 ? s[4 + i] : s[i], send = b4 ? s[i] : s[4 + i];
+            a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+        }
+        float b[2];
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+            const float keep = b3 ? a[2 + i] : a[i], send = b3 ? a[i] : a[2 + i];
+            b[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+        }
+        const float keep = b2 ? b[1] : b[0], send = b2 ? b[0] : b[1];
+        float v = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        return v;
     }
-}
-
-// 3-bit pair table: entry p = (a2 b2 a1 b1 a0 b0) -> half2( C[a], C[b] ); A = even k.
+};
 template <>
-__device__ __forceinline__ void stage_tables<3>(uint32_t tbl_addr, const __half *__restrict__ lut, uint32_t row0,
-                                                uint32_t N, int lane) {
-    const unsigned short *l16 = reinterpret_cast<const unsigned short *>(lut);
+struct BatchReduce<4> {
+    static constexpr int SH = 3;
+    __device__ __forceinline__ static float run(const float (&s)[4], int lane) { return batch_reduce<4>(s, lane); }
+};
+template <>
+struct BatchReduce<2> {
+    static constexpr int SH = 4;
+    __device__ __forceinline__ static float run(const float (&s)[2], int lane) { return batch_reduce<2>(s, lane); }
+};
+
+// ------------------------------------------------------------------------------------------------
+// Codebook expansion.  Every lane first fetches the lut words it needs for a stage (prefetched one
+// stage ahead, see the main loop), then writes its share of the warp's tables.
+// ------------------------------------------------------------------------------------------------
+template <int BITS, int RS>
+struct Tables;
+
+// 2-bit: entry p = (hA hB lA lB) -> half2( C[2hA+lA], C[2hB+lB] ), A = even k (low half).
+template <int RS>
+struct Tables<2, RS> {
+    static constexpr int IT = (RS + 1) / 2;  // lane covers row it*2 + (lane >> 4), entry lane & 15
+    struct Regs {
+        uint2 c[IT];
+    };
+    __device__ __forceinline__ static void fetch(Regs &r, const __half *__restrict__ lut, uint32_t row0, uint32_t N,
+                                                 int lane) {
 #pragma unroll
-    for (int r = 0; r < FastCfg<3>::RB; r++) {
-        const uint32_t row = min(row0 + r, N - 1);
-#pragma unroll
-        for (int h = 0; h < 2; h++) {
-            const int p = lane + 32 * h;
-            const uint32_t a = ((p >> 5) & 1) * 4 + ((p >> 3) & 1) * 2 + ((p >> 1) & 1);
-            const uint32_t b = ((p >> 4) & 1) * 4 + ((p >> 2) & 1) * 2 + (p & 1);
-            const uint32_t ca = __ldg(l16 + (size_t)row * 8 + a), cb = __ldg(l16 + (size_t)row * 8 + b);
-            asm volatile("st.shared.b32 [%0], %1;" ::"r"(tbl_addr + r * 256 + p * 4), "r"(ca | (cb << 16)));
+        for (int it = 0; it < IT; it++) {
+            const uint32_t row = min(row0 + it * 2 + (lane >> 4), N - 1);
+            r.c[it] = __ldg(reinterpret_cast<const uint2 *>(lut + (size_t)row * 4));
         }
     }
-}
-
-// 4-bit scalar table: 16 halfs per row, copied verbatim.
-template <>
-__device__ __forceinline__ void stage_tables<4>(uint32_t tbl_addr, const __half *__restrict__ lut, uint32_t row0,
-                                                uint32_t N, int lane) {
-    const int r = lane >> 3, w = lane & 7;
-    if (r < FastCfg<4>::RB) {
-        const uint32_t row = min(row0 + r, N - 1);
-        const uint32_t v = __ldg(reinterpret_cast<const uint32_t *>(lut + (size_t)row * 16) + w);
-        asm volatile("st.shared.b32 [%0], %1;" ::"r"(tbl_addr + r * 32 + w * 4), "r"(v));
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-// One row x one slab for one lane: 128 weights (BITS LDG.128 worth) against the lane's 64 half2 x.
-// xr[(4c+q)*4 + e2] = half2( x[kb(c)+8q+2e2], x[kb(c)+8q+2e2+1] ).  ROW_OFF = r * ROW_TBL_BYTES.
-// ---------------------------------------------------------------------------------------------
-template <int BITS, int ROW_OFF>
-struct RowDot;
-
-template <int ROW_OFF>
-struct RowDot<2, ROW_OFF> {
-    __device__ __forceinline__ static float run(const uint4 (&pl)[2], const uint32_t (&xr)[64], uint32_t tbl_base) {
-        const uint32_t Hq[4] = {pl[0].x, pl[0].y, pl[0].z, pl[0].w};
-        const uint32_t Lq[4] = {pl[1].x, pl[1].y, pl[1].z, pl[1].w};
-        float acc = 0.f;
+    __device__ __forceinline__ static void store(const Regs &r, uint32_t tbl, int lane) {
+        const int p = lane & 15;
+        const uint32_t a = ((p >> 3) & 1) * 2 + ((p >> 1) & 1), b = ((p >> 2) & 1) * 2 + (p & 1);
+        const uint32_t sel = (2 * a) | ((2 * a + 1) << 4) | ((2 * b) << 8) | ((2 * b + 1) << 12);
 #pragma unroll
-        for (int q = 0; q < 4; q++) {
-            const uint32_t H = Hq[q], L = Lq[q];
-            // nibble m of zh = (H[4m+3] H[4m+2] L[4m+3] L[4m+2]); of zl = (H[4m+1] H[4m] L[4m+1] L[4m])
-            const uint32_t zh = bitsel(H, L >> 2, 0xCCCCCCCCu);
-            const uint32_t zl = bitsel(H << 2, L, 0xCCCCCCCCu);
-            // byte b of each word = 4 * pair-index (a complete table byte offset)
-            const uint32_t a0 = (zh << 2) & 0x3C3C3C3Cu;  // even nibbles of zh -> e2 = 2
-            const uint32_t a1 = (zh >> 2) & 0x3C3C3C3Cu;  // odd  nibbles of zh -> e2 = 0
-            const uint32_t a2 = (zl << 2) & 0x3C3C3C3Cu;  // even nibbles of zl -> e2 = 3
-            const uint32_t a3 = (zl >> 2) & 0x3C3C3C3Cu;  // odd  nibbles of zl -> e2 = 1
-            uint32_t s0 = 0u, s1 = 0u;
-#pragma unroll
-            for (int b = 0; b < 4; b++) {
-                const int c = 3 - b, xb = (4 * c + q) * 4;
-                const uint32_t sel = 0x7650u | b;
-                const uint32_t w0 = lds_b32_imm<ROW_OFF>(__byte_perm(a1, tbl_base, sel));
-                const uint32_t w1 = lds_b32_imm<ROW_OFF>(__byte_perm(a3, tbl_base, sel));
-                const uint32_t w2 = lds_b32_imm<ROW_OFF>(__byte_perm(a0, tbl_base, sel));
-                const uint32_t w3 = lds_b32_imm<ROW_OFF>(__byte_perm(a2, tbl_base, sel));
-                s0 = hfma2_u32(w0, xr[xb + 0], s0);
-                s1 = hfma2_u32(w1, xr[xb + 1], s1);
-                s0 = hfma2_u32(w2, xr[xb + 2], s0);
-                s1 = hfma2_u32(w3, xr[xb + 3], s1);
+        for (int it = 0; it < IT; it++) {
+            const int row = it * 2 + (lane >> 4);
+            if (row < RS) {
+                const uint32_t e = __byte_perm(r.c[it].x, r.c[it].y, sel);
+                asm volatile("st.shared.b32 [%0], %1;" ::"r"(tbl + row * 64 + p * 4), "r"(e) : "memory");
             }
-            acc += h2_sum_f32(hadd2_u32(s0, s1));
         }
-        return acc;
     }
 };
 
-template <int ROW_OFF>
-struct RowDot<3, ROW_OFF> {
-    __device__ __forceinline__ static float run(const uint4 (&pl)[3], const uint32_t (&xr)[64], uint32_t tbl_base) {
-        const uint32_t P2q[4] = {pl[0].x, pl[0].y, pl[0].z, pl[0].w};
-        const uint32_t P1q[4] = {pl[1].x, pl[1].y, pl[1].z, pl[1].w};
-        const uint32_t P0q[4] = {pl[2].x, pl[2].y, pl[2].z, pl[2].w};
-        float acc = 0.f;
+// 3-bit: entry p = (a2 b2 a1 b1 a0 b0) -> half2( C[a], C[b] ), A = even k.
+// lane covers row (lane >> 2) + 8*it and the 16 entries p = (lane & 3) * 16 + 0..15 of it.
+template <int RS>
+struct Tables<3, RS> {
+    static constexpr int IT = (RS + 7) / 8;
+    struct Regs {
+        uint4 c[IT];
+    };
+    __device__ __forceinline__ static void fetch(Regs &r, const __half *__restrict__ lut, uint32_t row0, uint32_t N,
+                                                 int lane) {
 #pragma unroll
-        for (int q = 0; q < 4; q++) {
-            const uint32_t P2 = P2q[q], P1 = P1q[q], P0 = P0q[q];
-            // target j: byte b = (P2[p+1] P2[p] P1[p+1] P1[p] P0[p+1] P0[p] 0 0), p = 8b+2j -> x pair e2 = 3-j
-            uint32_t t[4];
-            t[0] = bitsel(P2 << 6, bitsel(P1 << 4, P0 << 2, 0x30303030u), 0xC0C0C0C0u) & 0xFCFCFCFCu;
-            t[1] = bitsel(P2 << 4, bitsel(P1 << 2, P0, 0x30303030u), 0xC0C0C0C0u) & 0xFCFCFCFCu;
-            t[2] = bitsel(P2 << 2, bitsel(P1, P0 >> 2, 0x30303030u), 0xC0C0C0C0u) & 0xFCFCFCFCu;
-            t[3] = bitsel(P2, bitsel(P1 >> 2, P0 >> 4, 0x30303030u), 0xC0C0C0C0u) & 0xFCFCFCFCu;
-            uint32_t s0 = 0u, s1 = 0u;
-#pragma unroll
-            for (int b = 0; b < 4; b++) {
-                const int c = 3 - b, xb = (4 * c + q) * 4;
-                const uint32_t sel = 0x7650u | b;
-                const uint32_t w0 = lds_b32_imm<ROW_OFF>(__byte_perm(t[3], tbl_base, sel));
-                const uint32_t w1 = lds_b32_imm<ROW_OFF>(__byte_perm(t[2], tbl_base, sel));
-                const uint32_t w2 = lds_b32_imm<ROW_OFF>(__byte_perm(t[1], tbl_base, sel));
-                const uint32_t w3 = lds_b32_imm<ROW_OFF>(__byte_perm(t[0], tbl_base, sel));
-                s0 = hfma2_u32(w0, xr[xb + 0], s0);
-                s1 = hfma2_u32(w1, xr[xb + 1], s1);
-                s0 = hfma2_u32(w2, xr[xb + 2], s0);
-                s1 = hfma2_u32(w3, xr[xb + 3], s1);
-            }
-            acc += h2_sum_f32(hadd2_u32(s0, s1));
+        for (int it = 0; it < IT; it++) {
+            const uint32_t row = min(row0 + it * 8 + (lane >> 2), N - 1);
+            r.c[it] = __ldg(reinterpret_cast<const uint4 *>(lut + (size_t)row * 8));
         }
-        return acc;
     }
-};
-
-template <int ROW_OFF>
-struct RowDot<4, ROW_OFF> {
-    __device__ __forceinline__ static float run(const uint4 (&pl)[4], const uint32_t (&xr)[64], uint32_t tbl_base) {
-        const uint32_t P3q[4] = {pl[0].x, pl[0].y, pl[0].z, pl[0].w};
-        const uint32_t P2q[4] = {pl[1].x, pl[1].y, pl[1].z, pl[1].w};
-        const uint32_t P1q[4] = {pl[2].x, pl[2].y, pl[2].z, pl[2].w};
-        const uint32_t P0q[4] = {pl[3].x, pl[3].y, pl[3].z, pl[3].w};
-        float acc = 0.f;
+    __device__ __forceinline__ static uint32_t pick(const uint4 &c, uint32_t idx) {  // half idx (0..7) -> low 16 bits
+        const uint32_t lo = (idx & 4) ? c.z : c.x, hi = (idx & 4) ? c.w : c.y;     // halfs 0..3 or 4..7
+        const uint32_t w = (idx & 2) ? hi : lo;
+        return (idx & 1) ? (w >> 16) : (w & 0xffffu);
+    }
+    __device__ __forceinline__ static void store(const Regs &r, uint32_t tbl, int lane) {
 #pragma unroll
-        for (int q = 0; q < 4; q++) {
-            const uint32_t P3 = P3q[q], P2 = P2q[q], P1 = P1q[q], P0 = P0q[q];
-            __half s[4] = {__ushort_as_half(0), __ushort_as_half(0), __ushort_as_half(0), __ushort_as_half(0)};
+        for (int it = 0; it < IT; it++) {
+            const int row = it * 8 + (lane >> 2);
+            if (row < RS) {
+                const uint32_t a_hi = (lane >> 1) & 1, b_hi = lane & 1;  // p bits 5,4 are fixed per lane
 #pragma unroll
-            for (int sft = 0; sft < 4; sft++) {
-                // nibble m of y = 4-bit index (P3 P2 P1 P0) of the weight at bit position 4m+sft
-                uint32_t y;
-                if (sft == 3)
-                    y = bitsel(P3, bitsel(P2 >> 1, bitsel(P1 >> 2, P0 >> 3, 0x22222222u), 0x44444444u), 0x88888888u);
-                else if (sft == 2)
-                    y = bitsel(P3 << 1, bitsel(P2, bitsel(P1 >> 1, P0 >> 2, 0x22222222u), 0x44444444u), 0x88888888u);
-                else if (sft == 1)
-                    y = bitsel(P3 << 2, bitsel(P2 << 1, bitsel(P1, P0 >> 1, 0x22222222u), 0x44444444u), 0x88888888u);
-                else
-                    y = bitsel(P3 << 3, bitsel(P2 << 2, bitsel(P1 << 1, P0, 0x22222222u), 0x44444444u), 0x88888888u);
-                // byte b = 2*index.  ylo: bit position 8b+sft   -> k offset 31-8b-sft -> c = 3-b, e = 7-sft
-                //                    yhi: bit position 8b+4+sft -> k offset 27-8b-sft -> c = 3-b, e = 3-sft
-                const uint32_t ylo = (y << 1) & 0x1E1E1E1Eu, yhi = (y >> 3) & 0x1E1E1E1Eu;
+                for (int e = 0; e < 16; e += 4) {
+                    uint32_t v[4];
 #pragma unroll
-                for (int b = 0; b < 4; b++) {
-                    const int c = 3 - b, xb = (4 * c + q) * 4;
-                    const uint32_t sel = 0x7650u | b;
-                    const int e_lo = 7 - sft, e_hi = 3 - sft;
-                    const __half wl = __ushort_as_half((unsigned short)lds_u16_imm<ROW_OFF>(__byte_perm(ylo, tbl_base, sel)));
-                    const __half wh = __ushort_as_half((unsigned short)lds_u16_imm<ROW_OFF>(__byte_perm(yhi, tbl_base, sel)));
-                    const __half2 xl = *reinterpret_cast<const __half2 *>(&xr[xb + e_lo / 2]);
-                    const __half2 xh = *reinterpret_cast<const __half2 *>(&xr[xb + e_hi / 2]);
-                    s[sft] = __hfma(wl, (e_lo & 1) ? __high2half(xl) : __low2half(xl), s[sft]);
-                    s[(sft + 2) & 3] = __hfma(wh, (e_hi & 1) ? __high2half(xh) : __low2half(xh), s[(sft + 2) & 3]);
+                    for (int f = 0; f < 4; f++) {
+                        const int lowp = e + f;  // p bits 3..0 = (a1 b1 a0 b0)
+                        const uint32_t a = a_hi * 4 + ((lowp >> 3) & 1) * 2 + ((lowp >> 1) & 1);
+                        const uint32_t b = b_hi * 4 + ((lowp >> 2) & 1) * 2 + (lowp & 1);
+                        v[f] = pick(r.c[it], a) | (pick(r.c[it], b) << 16);
+                    }
+                    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(tbl + row * 256 + (lane & 3) * 64 + e * 4),
+                                 "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3])
+                                 : "memory");
                 }
             }
-            acc += (__half2float(s[0]) + __half2float(s[1])) + (__half2float(s[2]) + __half2float(s[3]));
         }
-        return acc;
     }
 };
 
-// ---------------------------------------------------------------------------------------------
-// Kernel
-// ---------------------------------------------------------------------------------------------
-struct FastParams {
-    const __half *x;      // [K]
-    const uint4 *W;       // [bits][N][K/128] as uint4
-    const __half *lut;    // [N][2^bits]
-    __half *out;          // [N] or nullptr
-    float *partial;       // [N] or nullptr
-    uint32_t N, K;
-    uint32_t nslab;       // ceil(K/4096)
-    uint32_t groups;      // row groups per CTA (warps per CTA = groups * nslab)
+// 4-bit: the 16 halfs of each row, verbatim.  lane covers row (lane >> 2) + 8*it, 8-byte piece lane & 3.
+template <int RS>
+struct Tables<4, RS> {
+    static constexpr int IT = (RS + 7) / 8;
+    struct Regs {
+        uint2 c[IT];
+    };
+    __device__ __forceinline__ static void fetch(Regs &r, const __half *__restrict__ lut, uint32_t row0, uint32_t N,
+                                                 int lane) {
+#pragma unroll
+        for (int it = 0; it < IT; it++) {
+            const uint32_t row = min(row0 + it * 8 + (lane >> 2), N - 1);
+            r.c[it] = __ldg(reinterpret_cast<const uint2 *>(lut + (size_t)row * 16) + (lane & 3));
+        }
+    }
+    __device__ __forceinline__ static void store(const Regs &r, uint32_t tbl, int lane) {
+#pragma unroll
+        for (int it = 0; it < IT; it++) {
+            const int row = it * 8 + (lane >> 2);
+            if (row < RS)
+                asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(tbl + row * 32 + (lane & 3) * 8), "r"(r.c[it].x),
+                             "r"(r.c[it].y)
+                             : "memory");
+        }
+    }
 };
 
-// Shared memory: [ per-warp tables (256B aligned) | x slabs, swizzled 16B units | cross-slab reduction ]
-template <int BITS>
-__global__ void __launch_bounds__(256) gemv_fast_kernel(const FastParams p) {
-    constexpr int RB = FastCfg<BITS>::RB;
-    constexpr int ROWB = FastCfg<BITS>::ROW_TBL_BYTES;
-    constexpr int WTB = FastWarpTbl<BITS>::BYTES;
+// ------------------------------------------------------------------------------------------------
+// One word per plane (32 weights of one row, this lane's share of a chunk) against 16 half2 of x.
+// xr[4c + e2] = half2( x[k0(c) + 2 e2], x[k0(c) + 2 e2 + 1] ), k0(c) = i*1024 + c*8*eff + 8t.
+// ROW_OFF = r * ROW_TBL_BYTES selects the row's table by an LDS immediate.
+// ------------------------------------------------------------------------------------------------
+template <int BITS, int ROW_OFF>
+struct WordDot;
+
+template <int ROW_OFF>
+struct WordDot<2, ROW_OFF> {
+    __device__ __forceinline__ static float run(const uint32_t (&pw)[2], const uint32_t *xr, uint32_t tbl) {
+        const uint32_t H = pw[0], L = pw[1];
+        // nibble m of zh = (H[4m+3] H[4m+2] L[4m+3] L[4m+2]); of zl = (H[4m+1] H[4m] L[4m+1] L[4m])
+        const uint32_t zh = bitsel(H, L >> 2, 0xCCCCCCCCu);
+        const uint32_t zl = bitsel(H << 2, L, 0xCCCCCCCCu);
+        // byte b of each word = 4 * pair index = a complete table byte offset; byte b <-> c = 3 - b
+        const uint32_t a0 = (zh << 2) & 0x3C3C3C3Cu;  // even nibbles of zh -> pair e2 = 2
+        const uint32_t a1 = (zh >> 2) & 0x3C3C3C3Cu;  // odd  nibbles of zh -> pair e2 = 0
+        const uint32_t a2 = (zl << 2) & 0x3C3C3C3Cu;  // even nibbles of zl -> pair e2 = 3
+        const uint32_t a3 = (zl >> 2) & 0x3C3C3C3Cu;  // odd  nibbles of zl -> pair e2 = 1
+        uint32_t s0 = 0u, s1 = 0u;
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+            const int xb = 4 * (3 - b);
+            const uint32_t sel = 0x7650u | b;
+            const uint32_t w0 = lds_b32_imm<ROW_OFF>(__byte_perm(a1, tbl, sel));
+            const uint32_t w1 = lds_b32_imm<ROW_OFF>(__byte_perm(a3, tbl, sel));
+            const uint32_t w2 = lds_b32_imm<ROW_OFF>(__byte_perm(a0, tbl, sel));
+            const uint32_t w3 = lds_b32_imm<ROW_OFF>(__byte_perm(a2, tbl, sel));
+            s0 = hfma2_u32(w0, xr[xb + 0], s0);
+            s1 = hfma2_u32(w1, xr[xb + 1], s1);
+            s0 = hfma2_u32(w2, xr[xb + 2], s0);
+            s1 = hfma2_u32(w3, xr[xb + 3], s1);
+        }
+        return h2_sum_f32(hadd2_u32(s0, s1));
+    }
+};
+
+template <int ROW_OFF>
+struct WordDot<3, ROW_OFF> {
+    __device__ __forceinline__ static float run(const uint32_t (&pw)[3], const uint32_t *xr, uint32_t tbl) {
+        const uint32_t P2 = pw[0], P1 = pw[1], P0 = pw[2];
+        // target j: byte b = (P2[p+1] P2[p] P1[p+1] P1[p] P0[p+1] P0[p] 0 0), p = 8b+2j  -> x pair e2 = 3-j
+        uint32_t t[4];
+        t[0] = bitsel(P2 << 6, bitsel(P1 << 4, P0 << 2, 0x30303030u), 0xC0C0C0C0u) & 0xFCFCFCFCu;
+        t[1] = bitsel(P2 << 4, bitsel(P1 << 2, P0, 0x30303030u), 0xC0C0C0C0u) & 0xFCFCFCFCu;
+        t[2] = bitsel(P2 << 2, bitsel(P1, P0 >> 2, 0x30303030u), 0xC0C0C0C0u) & 0xFCFCFCFCu;
+        t[3] = bitsel(P2, bitsel(P1 >> 2, P0 >> 4, 0x30303030u), 0xC0C0C0C0u) & 0xFCFCFCFCu;
+        uint32_t s0 = 0u, s1 = 0u;
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+            const int xb = 4 * (3 - b);
+            const uint32_t sel = 0x7650u | b;
+            const uint32_t w0 = lds_b32_imm<ROW_OFF>(__byte_perm(t[3], tbl, sel));
+            const uint32_t w1 = lds_b32_imm<ROW_OFF>(__byte_perm(t[2], tbl, sel));
+            const uint32_t w2 = lds_b32_imm<ROW_OFF>(__byte_perm(t[1], tbl, sel));
+            const uint32_t w3 = lds_b32_imm<ROW_OFF>(__byte_perm(t[0], tbl, sel));
+            s0 = hfma2_u32(w0, xr[xb + 0], s0);
+            s1 = hfma2_u32(w1, xr[xb + 1], s1);
+            s0 = hfma2_u32(w2, xr[xb + 2], s0);
+            s1 = hfma2_u32(w3, xr[xb + 3], s1);
+        }
+        return h2_sum_f32(hadd2_u32(s0, s1));
+    }
+};
+
+template <int ROW_OFF>
+struct WordDot<4, ROW_OFF> {
+    __device__ __forceinline__ static float run(const uint32_t (&pw)[4], const uint32_t *xr, uint32_t tbl) {
+        const uint32_t P3 = pw[0], P2 = pw[1], P1 = pw[2], P0 = pw[3];
+        __half s[4] = {__ushort_as_half(0), __ushort_as_half(0), __ushort_as_half(0), __ushort_as_half(0)};
+#pragma unroll
+        for (int sft = 0; sft < 4; sft++) {
+            // nibble m of y = 4-bit index (P3 P2 P1 P0) of the weight at bit position 4m+sft
+            uint32_t y;
+            if (sft == 3)
+                y = bitsel(P3, bitsel(P2 >> 1, bitsel(P1 >> 2, P0 >> 3, 0x22222222u), 0x44444444u), 0x88888888u);
+            else if (sft == 2)
+                y = bitsel(P3 << 1, bitsel(P2, bitsel(P1 >> 1, P0 >> 2, 0x22222222u), 0x44444444u), 0x88888888u);
+            else if (sft == 1)
+                y = bitsel(P3 << 2, bitsel(P2 << 1, bitsel(P1, P0 >> 1, 0x22222222u), 0x44444444u), 0x88888888u);
+            else
+                y = bitsel(P3 << 3, bitsel(P2 << 2, bitsel(P1 << 1, P0, 0x22222222u), 0x44444444u), 0x88888888u);
+            // byte b = 2*index.  ylo: bit 8b+sft   -> k offset 31-8b-sft -> c = 3-b, e = 7-sft
+            //                    yhi: bit 8b+4+sft -> k offset 27-8b-sft -> c = 3-b, e = 3-sft
+            const uint32_t ylo = (y << 1) & 0x1E1E1E1Eu, yhi = (y >> 3) & 0x1E1E1E1Eu;
+#pragma unroll
+            for (int b = 0; b < 4; b++) {
+                const int xb = 4 * (3 - b);
+                const uint32_t sel = 0x7650u | b;
+                const int e_lo = 7 - sft, e_hi = 3 - sft;
+                const __half wl = __ushort_as_half((unsigned short)lds_u16_imm<ROW_OFF>(__byte_perm(ylo, tbl, sel)));
+                const __half wh = __ushort_as_half((unsigned short)lds_u16_imm<ROW_OFF>(__byte_perm(yhi, tbl, sel)));
+                const __half2 xl = *reinterpret_cast<const __half2 *>(&xr[xb + e_lo / 2]);
+                const __half2 xh = *reinterpret_cast<const __half2 *>(&xr[xb + e_hi / 2]);
+                s[sft] = __hfma(wl, (e_lo & 1) ? __high2half(xl) : __low2half(xl), s[sft]);
+                s[(sft + 2) & 3] = __hfma(wh, (e_hi & 1) ? __high2half(xh) : __low2half(xh), s[(sft + 2) & 3]);
+            }
+        }
+        return (__half2float(s[0]) + __half2float(s[1])) + (__half2float(s[2]) + __half2float(s[3]));
+    }
+};
+
+// compile-time unrolled loop over the RS rows of a stage (the row index must be a template constant so
+// that the table offset becomes an LDS immediate)
+template <int BITS, int RS, int R>
+struct RowLoop {
+    __device__ __forceinline__ static void run(float (&acc)[RS], uint32_t rows, uint32_t stage, uint32_t row_bytes,
+                                               uint32_t woff, const uint32_t *xr, uint32_t tbl) {
+        if ((uint32_t)R < rows) {  // warp-uniform
+            uint32_t pw[BITS];
+#pragma unroll
+            for (int j = 0; j < BITS; j++) pw[j] = lds_b32(stage + (j * RS + R) * row_bytes + woff);
+            acc[R] += WordDot<BITS, R * FastCfg<BITS>::ROW_TBL_BYTES>::run(pw, xr, tbl);
+        }
+        RowLoop<BITS, RS, R + 1>::run(acc, rows, stage, row_bytes, woff, xr, tbl);
+    }
+};
+template <int BITS, int RS>
+struct RowLoop<BITS, RS, RS> {
+    __device__ __forceinline__ static void run(float (&)[RS], uint32_t, uint32_t, uint32_t, uint32_t, const uint32_t *,
+                                               uint32_t) {}
+};
+
+// ------------------------------------------------------------------------------------------------
+// Kernel
+// ------------------------------------------------------------------------------------------------
+struct FastParams {
+    const __half *x;         // [K]
+    const uint8_t *W;        // [bits][N][K/8] bytes
+    const __half *lut;       // [N][2^bits]
+    __half *out;             // [N] or nullptr
+    float *partial;          // [N] or nullptr
+    uint32_t N, K;
+    uint32_t nwk;            // consumer warps per row group = ceil(nchunk / CPW)
+    uint32_t groups;         // row groups per CTA; consumer warps = groups * nwk; +1 producer warp
+    uint32_t nslots;         // ring slots (multiple of groups)
+    uint32_t stage_bytes;    // RS * BITS * K/8
+};
+
+// smem: [barriers 2*nslots*8 | pad->256 | tables (per consumer warp) | ring nslots*stage_bytes | red floats]
+template <int BITS, int CPW, int RS>
+__global__ void __launch_bounds__(544, 1) gemv_fast_kernel(const FastParams p) {
+    constexpr int WTB = FastWarpTbl<BITS, RS>::BYTES;
+    using Tb = Tables<BITS, RS>;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int nwarps = blockDim.x >> 5;
-    const uint32_t nslab = p.nslab;
-    const uint32_t g = warp / nslab, s = warp - g * nslab;
-    const uint32_t words = p.K >> 5;          // words per (row, plane)
-    const uint32_t vecs = words >> 2;         // uint4 per (row, plane)
+    const uint32_t nwk = p.nwk, G = p.groups, NS = p.nslots;
+    const uint32_t ncons = G * nwk;
+    const uint32_t K = p.K, N = p.N;
+    const uint32_t row_bytes = K >> 3;  // bytes of one (row, plane)
 
-    const uint32_t smem_base = (smem_u32(smem_raw) + 255u) & ~255u;
-    const uint32_t tbl_base = smem_base + warp * WTB;
-    const uint32_t x_base = smem_base + nwarps * WTB;
-    float *red = reinterpret_cast<float *>(smem_raw + (x_base - smem_u32(smem_raw)) + nslab * 8192u);
+    const uint32_t smem0 = smem_u32(smem_raw);
+    const uint32_t bar_full = smem0, bar_empty = smem0 + NS * 8u;
+    const uint32_t tbl0 = (smem0 + 2u * NS * 8u + 255u) & ~255u;
+    const uint32_t ring0 = tbl0 + ncons * WTB;
+    float *red = reinterpret_cast<float *>(smem_raw + (ring0 - smem0) + NS * p.stage_bytes);
 
-    // rows of this group
-    const uint32_t total_groups = gridDim.x * p.groups;
-    const uint32_t gid = blockIdx.x * p.groups + g;
-    const uint32_t r_begin = (uint32_t)(((uint64_t)p.N * gid) / total_groups);
-    const uint32_t r_end = (uint32_t)(((uint64_t)p.N * (gid + 1)) / total_groups);
+    // rows of this CTA, stages of RS rows
+    const uint32_t r_begin = (uint32_t)(((uint64_t)N * blockIdx.x) / gridDim.x);
+    const uint32_t r_end = (uint32_t)(((uint64_t)N * (blockIdx.x + 1)) / gridDim.x);
+    const uint32_t nrows = r_end - r_begin;
+    const uint32_t nstages = (nrows + RS - 1) / RS;
 
-    const uint32_t v0 = s * 32u + lane;       // this lane's uint4 index inside a (row, plane)
-    const bool active = v0 < vecs;
-
-    // ---- independent of x: first batch of bit-planes + codebooks (overlaps the previous kernel under PDL)
-    uint4 pl[RB][BITS];
-    auto load_batch = [&](uint32_t row0) {
-#pragma unroll
-        for (int r = 0; r < RB; r++) {
-            const uint32_t row = min(row0 + r, p.N - 1);
-#pragma unroll
-            for (int j = 0; j < BITS; j++)
-                if (active) pl[r][j] = ldg_stream_v4(p.W + ((size_t)j * p.N + row) * vecs + v0);
+    if (threadIdx.x == 0) {
+        for (uint32_t s = 0; s < NS; s++) {
+            mbar_init(bar_full + 8u * s, 1u);
+            mbar_init(bar_empty + 8u * s, nwk);
         }
-    };
-    if (r_begin < r_end) {
-        load_batch(r_begin);
-        stage_tables<BITS>(tbl_base, p.lut, r_begin, p.N, lane);
-    }
-
-    // ---- x: global -> swizzled smem units -> registers
-    pdl_wait_prior_grid();
-    {
-        const uint32_t units = p.K >> 3;  // 16-byte units of x
-        const uint32_t full = p.K >> 10;
-        const uint32_t eff_tail = (p.K & 1023u) >> 5;
-        for (uint32_t u = threadIdx.x; u < units; u += blockDim.x) {
-            const uint32_t k = u << 3;
-            const uint32_t i = k >> 10, r = k & 1023u;
-            const uint32_t eff = (i < full) ? 32u : eff_tail;
-            const uint32_t c = r / (8u * eff), t = (r - c * 8u * eff) >> 3;
-            const uint32_t w = i * 32u + t;
-            const uint32_t sl = w >> 7, L = (w & 127u) >> 2, q = w & 3u;
-            const uint32_t j = 4u * c + q;
-            const uint4 v = __ldg(reinterpret_cast<const uint4 *>(p.x) + u);
-            sts_v4(x_base + ((sl * 32u + L) * 16u + (j ^ (L & 7u))) * 16u, v);
-        }
+        mbar_fence_init();
     }
     __syncthreads();
-    pdl_launch_dependents();
 
-    uint32_t xr[64];
-    if (active) {
+    if ((uint32_t)warp == ncons) {
+        // ===================== producer: stream [r_begin, r_end) through the ring =====================
+        if (lane == 0) {
+            const uint64_t pol = l2_policy_evict_first();
+            for (uint32_t s = 0; s < nstages; s++) {
+                const uint32_t slot = s % NS, use = s / NS;
+                if (use > 0) mbar_wait(bar_empty + 8u * slot, (use - 1u) & 1u);
+                const uint32_t row0 = r_begin + s * RS;
+                const uint32_t rows = min((uint32_t)RS, r_end - row0);
+                const uint32_t bytes = rows * row_bytes;
+                mbar_arrive_expect_tx(bar_full + 8u * slot, bytes * BITS);
 #pragma unroll
-        for (int j = 0; j < 16; j++) {
-            const uint4 v = lds_v4(x_base + ((s * 32u + lane) * 16u + (j ^ (lane & 7))) * 16u);
-            xr[4 * j + 0] = v.x, xr[4 * j + 1] = v.y, xr[4 * j + 2] = v.z, xr[4 * j + 3] = v.w;
+                for (int j = 0; j < BITS; j++)
+                    bulk_g2s(ring0 + slot * p.stage_bytes + j * RS * row_bytes,
+                             p.W + ((size_t)j * N + row0) * row_bytes, bytes, bar_full + 8u * slot, pol);
+            }
+        }
+    } else {
+        // ===================== consumers =====================
+        const uint32_t g = warp / nwk, wk = warp - g * nwk;
+        const uint32_t tbl = tbl0 + warp * WTB;
+        const uint32_t nchunk = (K + 1023u) >> 10;
+
+        // codebook rows of this group's first stage (independent of the previous kernel)
+        typename Tb::Regs lr;
+        if (g < nstages) Tb::fetch(lr, p.lut, r_begin + g * RS, N, lane);
+
+        // x -> registers (produced by the previous kernel on the stream: wait for it under PDL)
+        pdl_wait_prior_grid();
+        uint32_t xr[CPW][16];
+        bool act[CPW];
+        uint32_t woff[CPW];  // byte offset of this lane's word inside a (row, plane)
+#pragma unroll
+        for (int cc = 0; cc < CPW; cc++) {
+            const uint32_t i = wk * CPW + cc;
+            const uint32_t eff = (i < nchunk) ? chunk_eff(K, i) : 0u;
+            act[cc] = (uint32_t)lane < eff;
+            woff[cc] = (i * 32u + lane) * 4u;
+            if (act[cc]) {
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    const uint4 v = __ldg(reinterpret_cast<const uint4 *>(p.x + i * 1024u + c * 8u * eff + 8u * lane));
+                    xr[cc][4 * c + 0] = v.x, xr[cc][4 * c + 1] = v.y, xr[cc][4 * c + 2] = v.z, xr[cc][4 * c + 3] = v.w;
+                }
+            }
+        }
+        pdl_launch_dependents();
+
+        for (uint32_t s = g; s < nstages; s += G) {
+            const uint32_t slot = s % NS, use = s / NS;
+            const uint32_t row0 = r_begin + s * RS;
+            const uint32_t rows = min((uint32_t)RS, r_end - row0);
+            // tables for this stage from the prefetched codebook rows; prefetch the next stage's rows
+            __syncwarp();
+            Tb::store(lr, tbl, lane);
+            if (s + G < nstages) Tb::fetch(lr, p.lut, row0 + G * RS, N, lane);
+            __syncwarp();
+            mbar_wait(bar_full + 8u * slot, use & 1u);
+
+            const uint32_t stage = ring0 + slot * p.stage_bytes;
+            float acc[RS];
+#pragma unroll
+            for (int r = 0; r < RS; r++) acc[r] = 0.f;
+#pragma unroll
+            for (int cc = 0; cc < CPW; cc++)
+                if (act[cc]) RowLoop<BITS, RS, 0>::run(acc, rows, stage, row_bytes, woff[cc], xr[cc], tbl);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_empty + 8u * slot);
+
+            const float v = BatchReduce<RS>::run(acc, lane);
+            const int rl = lane >> BatchReduce<RS>::SH;
+            if ((lane & ((1 << BatchReduce<RS>::SH) - 1)) == 0 && (uint32_t)rl < rows)
+                red[(row0 - r_begin + rl) * nwk + wk] = v;
         }
     }
 
-    // ---- row batches
-    uint32_t parity = 0;
-    for (uint32_t row0 = r_begin; row0 < r_end; row0 += RB) {
-        if (row0 != r_begin) {
-            __syncwarp();
-            load_batch(row0);
-            stage_tables<BITS>(tbl_base, p.lut, row0, p.N, lane);
-        }
-        __syncwarp();
-
-        float sums[RB];
-#pragma unroll
-        for (int r = 0; r < RB; r++) sums[r] = 0.f;
-        if (active) {
-            sums[0] = RowDot<BITS, 0 * ROWB>::run(pl[0], xr, tbl_base);
-            if (RB > 1) sums[1 % RB] = RowDot<BITS, (1 % RB) * ROWB>::run(pl[1 % RB], xr, tbl_base);
-            if (RB > 2) sums[2 % RB] = RowDot<BITS, (2 % RB) * ROWB>::run(pl[2 % RB], xr, tbl_base);
-            if (RB > 3) sums[3 % RB] = RowDot<BITS, (3 % RB) * ROWB>::run(pl[3 % RB], xr, tbl_base);
-        }
-        float v = batch_reduce<RB>(sums, lane);
-        const int rl = batch_row_of_lane<RB>(lane);
-        const bool writer = batch_lane_is_writer<RB>(lane);
-        const uint32_t row = row0 + rl;
-        if (nslab > 1) {
-            float *rbuf = red + ((g * 2 + parity) * nslab) * RB;
-            if (writer) rbuf[s * RB + rl] = v;
-            asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "r"(nslab * 32u));
-            if (s == 0 && writer) {
-                v = rbuf[rl];
-                for (uint32_t ss = 1; ss < nslab; ss++) v += rbuf[ss * RB + rl];
-            }
-            parity ^= 1;
-        }
-        if (s == 0 && writer && row < r_end) {
-            if (p.out) p.out[row] = __float2half_rn(v);
-            if (p.partial) p.partial[row] = v;
-        }
+    __syncthreads();
+    // fixed-order combination of the per-chunk partial sums -> deterministic results
+    for (uint32_t r = threadIdx.x; r < nrows; r += blockDim.x) {
+        float v = red[r * nwk];
+        for (uint32_t w = 1; w < nwk; w++) v += red[r * nwk + w];
+        if (p.out) p.out[r_begin + r] = __float2half_rn(v);
+        if (p.partial) p.partial[r_begin + r] = v;
     }
 }
 
-template <int BITS>
-inline size_t fast_smem_bytes(uint32_t nslab, uint32_t groups) {
-    const size_t nwarps = (size_t)nslab * groups;
-    return 256 + nwarps * FastWarpTbl<BITS>::BYTES + (size_t)nslab * 8192 +
-           (nslab > 1 ? groups * 2 * nslab * FastCfg<BITS>::RB * sizeof(float) : 0) + 16;
+template <int BITS, int RS>
+inline size_t fast_smem_bytes(uint32_t ncons, uint32_t nslots, uint32_t stage_bytes, uint32_t rows_per_cta,
+                              uint32_t nwk) {
+    return 2 * (size_t)nslots * 8 + 256 + (size_t)ncons * FastWarpTbl<BITS, RS>::BYTES + (size_t)nslots * stage_bytes +
+           (size_t)rows_per_cta * nwk * sizeof(float) + 16;
 }
 
 }  // namespace apg

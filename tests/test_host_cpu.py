@@ -1,0 +1,107 @@
+"""CPU tests: the C-ABI library loads and exports every symbol include/*.h declares (no compute calls),
+the torch-facing layer validates arguments like the reference, the op is registered with the reference's
+schema, and the K-shard planner / re-packer is exact."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_capi_exports_every_declared_symbol():
+    from guidedquant_b200 import _lib
+
+    hdr = open(os.path.join(ROOT, "include", "apgemv_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(apg_[a-z0-9_]+)\s*\(", hdr))
+    assert {"apg_gemv", "apg_gemv_ex", "apg_dequant", "apg_version"} <= declared
+    path = _lib.build()
+    L = ctypes.CDLL(path)
+    for sym in sorted(declared):
+        assert hasattr(L, sym), f"{sym} declared in include/apgemv_b200.h but not exported"
+    assert set(_lib.EXPORTS) <= declared
+    L.apg_version.restype = ctypes.c_int
+    assert L.apg_version() >= 100
+    L.apg_status_string.restype = ctypes.c_char_p
+    assert b"Bitwidth" in L.apg_status_string(2)
+
+
+def test_capi_argument_validation_without_gpu():
+    """validation happens before any CUDA call, so it is checkable on a CPU-only box"""
+    from guidedquant_b200 import _lib
+
+    L = _lib.lib()
+    buf = (ctypes.c_uint8 * 4096)()
+    p = ctypes.addressof(buf)
+    p = (p + 63) & ~63
+    assert L.apg_gemv(None, p, p, p, 1, 4, 128, 2, None) == 1          # null
+    assert L.apg_gemv(p, p, p, p, 1, 4, 128, 9, None) == 2             # bits
+    assert L.apg_gemv(p, p, p, p, 9, 4, 128, 2, None) == 3             # batch
+    assert L.apg_gemv(p, p, p, p, 1, 4, 100, 2, None) == 4             # K % 32
+    assert L.apg_gemv(p, p, p, p, 1, 0, 128, 2, None) == 4             # N
+    assert L.apg_gemv(p + 2, p, p, p, 1, 4, 128, 2, None) == 5         # alignment of x
+    assert L.apg_gemv_ex(p, p, None, p, p, 1, 4, 128, 2, 0x80, 0, None) == 7   # unknown flag
+    assert L.apg_dequant(p, p, p, 4, 128, 1, None) == 2
+
+
+def test_python_layer_validates_like_the_reference():
+    from guidedquant_b200 import ap_gemv
+
+    x = torch.zeros((1, 1, 128), dtype=torch.float16)
+    q = torch.zeros((2, 8, 4), dtype=torch.int32)
+    lut = torch.zeros((8, 4), dtype=torch.float16)
+    out = torch.zeros((1, 1, 8), dtype=torch.float16)
+    with pytest.raises(RuntimeError, match="must be on GPU"):
+        ap_gemv.anyprec_gemv(x, out, q, lut, 2)
+    with pytest.raises(RuntimeError, match="Bitwidth must be between 2 and 8"):
+        ap_gemv.anyprec_gemv(x, out, q, lut, 1)
+    with pytest.raises(RuntimeError, match="Mismatched data types"):
+        ap_gemv.anyprec_gemv(x.float(), out, q, lut, 2)
+    with pytest.raises(RuntimeError, match="shape \\(batch_size, seq_len, hidden_size\\)"):
+        ap_gemv.anyprec_gemv(x[0], out, q, lut, 2)
+    with pytest.raises(RuntimeError):
+        ap_gemv.anyprec_dequant(q, lut, 2)   # CPU tensors
+
+
+def test_plugin_op_schema_matches_reference():
+    import guidedquant_b200.plugin as plugin  # noqa: F401
+
+    op = torch.ops.plugin.anyprec_gemv.default
+    s = str(op._schema)
+    # reference: anyprec_gemv(x, q_weight, lut, output, bitwidth) -> None, mutates output (inference/plugin.py:7-13)
+    assert "plugin::anyprec_gemv(Tensor x, Tensor q_weight, Tensor lut, Tensor(a3!) output, SymInt bitwidth) -> ()" == s or \
+        ("Tensor x, Tensor q_weight, Tensor lut" in s and "output" in s and "bitwidth" in s and s.endswith("-> ()")), s
+    assert callable(plugin.anyprec_dequant)
+
+
+def test_install_as_ap_gemv():
+    import sys
+
+    import guidedquant_b200
+
+    guidedquant_b200.install_as_ap_gemv()
+    import ap_gemv
+
+    assert ap_gemv is sys.modules["guidedquant_b200.ap_gemv"]
+    assert {"anyprec_gemv", "anyprec_dequant", "lutgemm_gemv"} <= set(dir(ap_gemv))
+
+
+def test_shard_bounds_and_repack_exact():
+    from guidedquant_b200 import pack as P
+
+    rng = np.random.default_rng(0)
+    for K, world, bits in ((28672, 8, 2), (14336, 4, 3), (8192, 2, 4), (11008, 2, 2), (4096, 8, 2)):
+        bounds = P.shard_bounds(K, world)
+        assert bounds[0][0] == 0 and bounds[-1][1] == K
+        assert all(b[1] == bounds[i + 1][0] for i, b in enumerate(bounds[:-1]))
+        assert all((b - a) % 128 == 0 and b > a for a, b in bounds)
+        idx = rng.integers(0, 1 << bits, size=(5, K), dtype=np.uint8)
+        q = P.pack_indices(idx, bits)
+        for a, b in bounds:
+            qs = P.shard_k(q, a, b)
+            assert qs.shape == (bits, 5, (b - a) // 32)
+            assert np.array_equal(P.unpack_indices(qs, bits), idx[:, a:b])

