@@ -49,6 +49,22 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "r"(parity)
         : "memory");
 }
+// producer-side wait: the single producer thread only needs to notice a free slot eventually, so it sleeps
+// between polls instead of burning issue slots the consumer warps need
+__device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    while (true) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (done) break;
+        __nanosleep(512);
+    }
+}
 // global -> shared 1-D bulk copy, completion (bytes) signalled on an mbarrier; L2 evict-first (streamed once)
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar, uint64_t pol) {
     asm volatile(
@@ -412,9 +428,9 @@ __global__ void __launch_bounds__(544, 1) gemv_fast_kernel(const FastParams p) {
         // ===================== producer: stream [r_begin, r_end) through the ring =====================
         if (lane == 0) {
             const uint64_t pol = l2_policy_evict_first();
+            uint32_t slot = 0, use = 0;
             for (uint32_t s = 0; s < nstages; s++) {
-                const uint32_t slot = s % NS, use = s / NS;
-                if (use > 0) mbar_wait(bar_empty + 8u * slot, (use - 1u) & 1u);
+                if (use > 0) mbar_wait_backoff(bar_empty + 8u * slot, (use - 1u) & 1u);
                 const uint32_t row0 = r_begin + s * RS;
                 const uint32_t rows = min((uint32_t)RS, r_end - row0);
                 const uint32_t bytes = rows * row_bytes;
@@ -423,6 +439,7 @@ __global__ void __launch_bounds__(544, 1) gemv_fast_kernel(const FastParams p) {
                 for (int j = 0; j < BITS; j++)
                     bulk_g2s(ring0 + slot * p.stage_bytes + j * RS * row_bytes,
                              p.W + ((size_t)j * N + row0) * row_bytes, bytes, bar_full + 8u * slot, pol);
+                if (++slot == NS) slot = 0, use++;
             }
         }
     } else {
@@ -456,14 +473,15 @@ __global__ void __launch_bounds__(544, 1) gemv_fast_kernel(const FastParams p) {
         }
         pdl_launch_dependents();
 
+        uint32_t slot = g, use = 0;  // NS is a multiple of G: a slot always serves the same group
         for (uint32_t s = g; s < nstages; s += G) {
-            const uint32_t slot = s % NS, use = s / NS;
             const uint32_t row0 = r_begin + s * RS;
             const uint32_t rows = min((uint32_t)RS, r_end - row0);
             // tables for this stage from the prefetched codebook rows; prefetch the next stage's rows
+            // (unconditional: the row index is clamped inside fetch, so no select/copy waits on the load)
             __syncwarp();
             Tb::store(lr, tbl, lane);
-            if (s + G < nstages) Tb::fetch(lr, p.lut, row0 + G * RS, N, lane);
+            Tb::fetch(lr, p.lut, row0 + G * RS, N, lane);
             __syncwarp();
             mbar_wait(bar_full + 8u * slot, use & 1u);
 
@@ -481,6 +499,8 @@ __global__ void __launch_bounds__(544, 1) gemv_fast_kernel(const FastParams p) {
             const int rl = lane >> BatchReduce<RS>::SH;
             if ((lane & ((1 << BatchReduce<RS>::SH) - 1)) == 0 && (uint32_t)rl < rows)
                 red[(row0 - r_begin + rl) * nwk + wk] = v;
+            slot += G;
+            if (slot >= NS) slot -= NS, use++;
         }
     }
 
