@@ -72,8 +72,9 @@ bool plan_fast(uint32_t N, uint32_t K, int ctas_per_sm, int sms, FastPlan *pl) {
     if (grid > max_grid) grid = max_grid;
     if (grid < 1) grid = 1;
     pl->grid = grid;
-    pl->rows_per_cta = (N + grid - 1) / grid + 1;
-    const uint32_t stages_per_cta = (pl->rows_per_cta + rs - 1) / rs;
+    const uint32_t tot_stages = (N + rs - 1) / rs;
+    const uint32_t stages_per_cta = (tot_stages + grid - 1) / grid;
+    pl->rows_per_cta = stages_per_cta * rs;
     // ring: as deep as the CTA's share needs, bounded so that c CTAs (+ a dependent kernel's) fit in 227 KB
     const size_t ring_budget = (c >= 2 ? 56u : 96u) * 1024u;
     uint32_t ns = (uint32_t)(ring_budget / pl->stage_bytes);

@@ -74,6 +74,16 @@ __device__ __forceinline__ uint32_t hadd2_u32(uint32_t a, uint32_t b) {
     asm("add.rn.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
     return d;
 }
+// acc + lo(v) + hi(v) with the adds done in fp32: two FHADD (mixed-precision add, PTX add.rn.f32.f16, sm_100+)
+__device__ __forceinline__ float acc_add_h2(float acc, uint32_t v) {
+    asm("{\n\t.reg .b16 lo, hi;\n\t"
+        "mov.b32 {lo, hi}, %1;\n\t"
+        "add.rn.f32.f16 %0, lo, %0;\n\t"
+        "add.rn.f32.f16 %0, hi, %0;\n\t}"
+        : "+f"(acc)
+        : "r"(v));
+    return acc;
+}
 __device__ __forceinline__ float h2_sum_f32(uint32_t v) {
     const __half2 h = *reinterpret_cast<const __half2 *>(&v);
     const float2 f = __half22float2(h);

@@ -260,7 +260,7 @@ struct WordDot;
 
 template <int ROW_OFF>
 struct WordDot<2, ROW_OFF> {
-    __device__ __forceinline__ static float run(const uint32_t (&pw)[2], const uint32_t *xr, uint32_t tbl) {
+    __device__ __forceinline__ static float run(float acc, const uint32_t (&pw)[2], const uint32_t *xr, uint32_t tbl) {
         const uint32_t H = pw[0], L = pw[1];
         // nibble m of zh = (H[4m+3] H[4m+2] L[4m+3] L[4m+2]); of zl = (H[4m+1] H[4m] L[4m+1] L[4m])
         const uint32_t zh = bitsel(H, L >> 2, 0xCCCCCCCCu);
@@ -284,13 +284,13 @@ struct WordDot<2, ROW_OFF> {
             s0 = hfma2_u32(w2, xr[xb + 2], s0);
             s1 = hfma2_u32(w3, xr[xb + 3], s1);
         }
-        return h2_sum_f32(hadd2_u32(s0, s1));
+        return acc_add_h2(acc, hadd2_u32(s0, s1));
     }
 };
 
 template <int ROW_OFF>
 struct WordDot<3, ROW_OFF> {
-    __device__ __forceinline__ static float run(const uint32_t (&pw)[3], const uint32_t *xr, uint32_t tbl) {
+    __device__ __forceinline__ static float run(float acc, const uint32_t (&pw)[3], const uint32_t *xr, uint32_t tbl) {
         const uint32_t P2 = pw[0], P1 = pw[1], P0 = pw[2];
         // target j: byte b = (P2[p+1] P2[p] P1[p+1] P1[p] P0[p+1] P0[p] 0 0), p = 8b+2j  -> x pair e2 = 3-j
         uint32_t t[4];
@@ -312,13 +312,13 @@ struct WordDot<3, ROW_OFF> {
             s0 = hfma2_u32(w2, xr[xb + 2], s0);
             s1 = hfma2_u32(w3, xr[xb + 3], s1);
         }
-        return h2_sum_f32(hadd2_u32(s0, s1));
+        return acc_add_h2(acc, hadd2_u32(s0, s1));
     }
 };
 
 template <int ROW_OFF>
 struct WordDot<4, ROW_OFF> {
-    __device__ __forceinline__ static float run(const uint32_t (&pw)[4], const uint32_t *xr, uint32_t tbl) {
+    __device__ __forceinline__ static float run(float acc, const uint32_t (&pw)[4], const uint32_t *xr, uint32_t tbl) {
         const uint32_t P3 = pw[0], P2 = pw[1], P1 = pw[2], P0 = pw[3];
         __half s[4] = {__ushort_as_half(0), __ushort_as_half(0), __ushort_as_half(0), __ushort_as_half(0)};
 #pragma unroll
@@ -349,29 +349,28 @@ struct WordDot<4, ROW_OFF> {
                 s[(sft + 2) & 3] = __hfma(wh, (e_hi & 1) ? __high2half(xh) : __low2half(xh), s[(sft + 2) & 3]);
             }
         }
-        return (__half2float(s[0]) + __half2float(s[1])) + (__half2float(s[2]) + __half2float(s[3]));
+        return acc + ((__half2float(s[0]) + __half2float(s[1])) + (__half2float(s[2]) + __half2float(s[3])));
     }
 };
 
 // compile-time unrolled loop over the RS rows of a stage (the row index must be a template constant so
-// that the table offset becomes an LDS immediate)
+// that the table offset becomes an LDS immediate).  All RS rows are always computed (no per-row branch,
+// so the compiler can interleave rows); rows past the end of a partial stage read stale-but-mapped ring
+// bytes and are discarded by the caller.
 template <int BITS, int RS, int R>
 struct RowLoop {
-    __device__ __forceinline__ static void run(float (&acc)[RS], uint32_t rows, uint32_t stage, uint32_t row_bytes,
-                                               uint32_t woff, const uint32_t *xr, uint32_t tbl) {
-        if ((uint32_t)R < rows) {  // warp-uniform
-            uint32_t pw[BITS];
+    __device__ __forceinline__ static void run(float (&acc)[RS], uint32_t pbase, uint32_t row_bytes, uint32_t plane_bytes,
+                                               const uint32_t *xr, uint32_t tbl) {
+        uint32_t pw[BITS];
 #pragma unroll
-            for (int j = 0; j < BITS; j++) pw[j] = lds_b32(stage + (j * RS + R) * row_bytes + woff);
-            acc[R] += WordDot<BITS, R * FastCfg<BITS>::ROW_TBL_BYTES>::run(pw, xr, tbl);
-        }
-        RowLoop<BITS, RS, R + 1>::run(acc, rows, stage, row_bytes, woff, xr, tbl);
+        for (int j = 0; j < BITS; j++) pw[j] = lds_b32(pbase + j * plane_bytes);
+        acc[R] = WordDot<BITS, R * FastCfg<BITS>::ROW_TBL_BYTES>::run(acc[R], pw, xr, tbl);
+        RowLoop<BITS, RS, R + 1>::run(acc, pbase + row_bytes, row_bytes, plane_bytes, xr, tbl);
     }
 };
 template <int BITS, int RS>
 struct RowLoop<BITS, RS, RS> {
-    __device__ __forceinline__ static void run(float (&)[RS], uint32_t, uint32_t, uint32_t, uint32_t, const uint32_t *,
-                                               uint32_t) {}
+    __device__ __forceinline__ static void run(float (&)[RS], uint32_t, uint32_t, uint32_t, const uint32_t *, uint32_t) {}
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -409,11 +408,14 @@ __global__ void __launch_bounds__(544, 1) gemv_fast_kernel(const FastParams p) {
     const uint32_t ring0 = tbl0 + ncons * WTB;
     float *red = reinterpret_cast<float *>(smem_raw + (ring0 - smem0) + NS * p.stage_bytes);
 
-    // rows of this CTA, stages of RS rows
-    const uint32_t r_begin = (uint32_t)(((uint64_t)N * blockIdx.x) / gridDim.x);
-    const uint32_t r_end = (uint32_t)(((uint64_t)N * (blockIdx.x + 1)) / gridDim.x);
+    // rows of this CTA: whole stages of RS rows (only the matrix's last stage can be partial)
+    const uint32_t tot_stages = (N + RS - 1) / RS;
+    const uint32_t s_begin = (uint32_t)(((uint64_t)tot_stages * blockIdx.x) / gridDim.x);
+    const uint32_t s_end = (uint32_t)(((uint64_t)tot_stages * (blockIdx.x + 1)) / gridDim.x);
+    const uint32_t nstages = s_end - s_begin;
+    const uint32_t r_begin = s_begin * RS;
+    const uint32_t r_end = min(s_end * RS, N);
     const uint32_t nrows = r_end - r_begin;
-    const uint32_t nstages = (nrows + RS - 1) / RS;
 
     if (threadIdx.x == 0) {
         for (uint32_t s = 0; s < NS; s++) {
@@ -491,7 +493,7 @@ __global__ void __launch_bounds__(544, 1) gemv_fast_kernel(const FastParams p) {
             for (int r = 0; r < RS; r++) acc[r] = 0.f;
 #pragma unroll
             for (int cc = 0; cc < CPW; cc++)
-                if (act[cc]) RowLoop<BITS, RS, 0>::run(acc, rows, stage, row_bytes, woff[cc], xr[cc], tbl);
+                if (act[cc]) RowLoop<BITS, RS, 0>::run(acc, stage + woff[cc], row_bytes, RS * row_bytes, xr[cc], tbl);
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_empty + 8u * slot);
 
