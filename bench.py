@@ -33,7 +33,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--model", default=None, help="default: llama3-8b on 1 GPU (BASELINE configs[1]); llama3-70b on >1")
+    ap.add_argument("--model", default=None, help="default llama3-8b (BASELINE configs[1]) at every N; llama3-70b / llama2-70b / llama2-7b selectable")
     ap.add_argument("--bits", type=int, default=2)
     ap.add_argument("--layers", type=int, default=None, help="override layer count (debug only; invalidates the number)")
     ap.add_argument("--no-pdl", action="store_true")
@@ -146,7 +146,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    model = a.model or ("llama3-8b" if max(world, a.gpus) == 1 else "llama3-70b")
+    model = a.model or "llama3-8b"  # same workload at every N so the scaling series is comparable (70B: --model llama3-70b)
     workload = f"{model} {a.bits}-bit bs=1 decode, ap_gemv hot path ({'4*L' if a.layers is None else a.layers} APLinear GEMVs/token chain)"
 
     if a.impl == "reference":
@@ -231,9 +231,17 @@ def main():
         t = torch.tensor([dt, dt_e2e], device="cuda", dtype=torch.float64)
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
         dt, dt_e2e = float(t[0]), float(t[1])
-    if rank != 0:
+    def finish():
+        # a live CUDA graph that captured NCCL kernels makes communicator teardown hang: drop the graph, sync,
+        # and leave without tearing the communicator down
         if world > 1:
-            torch.distributed.destroy_process_group()
+            chain.graph = None
+            torch.cuda.synchronize()
+            sys.stdout.flush()
+            os._exit(0)
+
+    if rank != 0:
+        finish()
         return
 
     tok_s = a.steps / dt
@@ -270,8 +278,7 @@ def main():
         except Exception as e:  # the GPU number must not be lost to a host-side failure
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e}"}
     print(json.dumps(line), flush=True)
-    if world > 1:
-        torch.distributed.destroy_process_group()
+    finish()
 
 
 if __name__ == "__main__":

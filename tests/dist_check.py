@@ -1,0 +1,110 @@
+"""Multi-process check of the sharded path (run under torchrun).
+    backend nccl (GPU box):  K-sharded GEMV partials (C-ABI, fp32) + all_reduce + round  ==  single-GPU GEMV
+                             N-sharded GEMV + all_gather                                  ==  single-GPU GEMV (bit-exact)
+                             sharded ApGemvChain graph replay == its eager execution
+    backend gloo (CPU):      the same shard planner / re-packer with the CPU oracle as the per-rank GEMV
+Exit code 0 = all checks passed on every rank."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from guidedquant_b200 import pack as P  # noqa: E402
+
+
+def main():
+    backend = sys.argv[1] if len(sys.argv) > 1 else "gloo"
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    if backend == "nccl":
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))
+        dist.init_process_group("nccl", device_id=torch.device("cuda", torch.cuda.current_device()))
+    else:
+        dist.init_process_group("gloo")
+    from oracle import oracle as O
+
+    def log(*a):
+        print(f"[rank {rank}]", *a, flush=True)
+
+    log("process group up", backend, world)
+
+    cases = [(64, 11008, 2), (32, 4096, 3), (48, 28672, 2), (40, 14336, 4)] if backend == "nccl" else [(8, 11008, 2), (8, 2048, 3)]
+    for (N, K, bits) in cases:
+        log("case", N, K, bits)
+        idx, q, lut, x = O.synth_layer(N, K, bits, seed=N + K)
+        k0, k1 = P.shard_bounds(K, world)[rank]
+        qs = P.shard_k(q, k0, k1)
+        assert np.array_equal(P.unpack_indices(qs, bits), idx[:, k0:k1])
+        xs = np.ascontiguousarray(x[:, :, k0:k1])
+        if backend == "gloo":
+            W = O.dequant(qs, lut, bits)
+            part = torch.from_numpy(O.gemv_f64(W, xs))
+            dist.all_reduce(part)
+            full = O.gemv_f64(O.dequant(q, lut, bits), x)
+            assert np.allclose(part.numpy(), full, rtol=1e-12, atol=1e-12), (N, K, bits)
+            continue
+        from guidedquant_b200 import _lib, ap_gemv
+
+        dev = torch.device("cuda", torch.cuda.current_device())
+        t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+        y_full = torch.zeros((1, 1, N), dtype=torch.float16, device=dev)
+        ap_gemv.anyprec_gemv(t(x), y_full, t(q), t(lut), bits)
+        # K-sharded
+        part = torch.zeros((1, N), dtype=torch.float32, device=dev)
+        y_tmp = torch.zeros((1, 1, N), dtype=torch.float16, device=dev)
+        ap_gemv.anyprec_gemv_ex(t(xs), y_tmp, t(qs), t(lut), bits, partial=part)
+        dist.all_reduce(part)
+        y_k = torch.zeros((1, 1, N), dtype=torch.float16, device=dev)
+        _lib.check(_lib.lib().apg_round_f32_to_f16(part.data_ptr(), y_k.data_ptr(), N, torch.cuda.current_stream().cuda_stream), "round")
+        y64 = torch.from_numpy(O.gemv_f64(O.dequant(q, lut, bits), x)).to(dev).reshape(1, 1, N)
+        e_full = float((y_full.double() - y64).abs().max() / y64.abs().max())
+        e_k = float((y_k.double() - y64).abs().max() / y64.abs().max())
+        assert e_full <= 1.2e-3 and e_k <= 1.2e-3, (N, K, bits, e_full, e_k)
+        # N-sharded
+        n0, n1 = N * rank // world, N * (rank + 1) // world
+        y_n = torch.zeros((1, 1, n1 - n0), dtype=torch.float16, device=dev)
+        ap_gemv.anyprec_gemv(t(x), y_n, t(q[:, n0:n1]), t(lut[n0:n1]), bits)
+        assert torch.equal(y_n, y_full[:, :, n0:n1]), "row sharding must be bit-exact"
+        if rank == 0:
+            print(f"N={N} K={K} bits={bits} world={world}: K-shard err {e_k:.2e} (single GPU {e_full:.2e}), N-shard bit-exact")
+    if backend == "nccl":
+        from guidedquant_b200.runtime import ApGemvChain
+
+        log("building sharded chain")
+        ch = ApGemvChain("tiny", bits=2, world_size=world, rank=rank, process_group=dist.group.WORLD)
+        log("chain built")
+        xh = torch.randn((1, 1, ch.cfg["dim"])).half()
+        dist.broadcast(xh_dev := xh.cuda(), 0)
+        y_eager = ch.eager_token(xh_dev)
+        torch.cuda.synchronize()
+        log("eager token done")
+        y_graph = ch.step_host(xh_dev.cpu().pin_memory()).clone()
+        assert torch.equal(y_eager.cpu(), y_graph), "graph replay differs from eager execution"
+        ys = [torch.zeros_like(y_eager) for _ in range(world)]
+        dist.all_gather(ys, y_eager)
+        assert all(torch.equal(ys[0], v) for v in ys), "ranks disagree on the all-reduced output"
+        assert torch.isfinite(y_eager).all() and float(y_eager.abs().max()) > 0
+        if rank == 0:
+            print("sharded ApGemvChain: graph == eager, all ranks agree", flush=True)
+        # a live CUDA graph that captured NCCL kernels makes communicator teardown hang: drop it first
+        ch.graph = None
+        del ch
+        torch.cuda.synchronize()
+    log("final barrier")
+    dist.barrier()
+    if backend == "nccl":
+        torch.cuda.synchronize()
+    if rank == 0:
+        print("DIST CHECK OK", flush=True)
+    if backend == "gloo":
+        dist.destroy_process_group()
+    else:
+        sys.stdout.flush()
+        os._exit(0)  # skip NCCL communicator teardown (can block after graph capture of collectives)
+
+
+if __name__ == "__main__":
+    main()
