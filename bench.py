@@ -38,6 +38,7 @@ def parse():
     ap.add_argument("--layers", type=int, default=None, help="override layer count (debug only; invalidates the number)")
     ap.add_argument("--no-pdl", action="store_true")
     ap.add_argument("--ctas", type=int, default=0)
+    ap.add_argument("--l2-prefetch", action="store_true", help="L2-prefetch the next Linear (measured slower on B200; off)")
     return ap.parse_args()
 
 
@@ -182,7 +183,7 @@ def main():
         pg = dist.group.WORLD
 
     chain = ApGemvChain(model, bits=a.bits, n_layer=a.layers, pdl=not a.no_pdl, world_size=world, rank=rank,
-                        process_group=pg, ctas_per_sm=a.ctas)
+                        process_group=pg, ctas_per_sm=a.ctas, l2_prefetch=a.l2_prefetch)
     chain.capture()
     d = chain.cfg["dim"]
     x_host = torch.randn((1, 1, d)).half().pin_memory()
@@ -258,7 +259,7 @@ def main():
             "workload": workload, "bits": a.bits, "gemv_launches_per_token": n_gemv,
             "parallelism": "single GPU" if world == 1 else f"tp{world}: wqkv/w1w3 N-sharded, wo/w2 K-sharded + NCCL all-reduce",
             "l2_policy": "inputs larger than L2: every GEMV reads its own distinct weights (%.2f GB/token/GPU), streamed evict-first" % (chain.weight_bytes() / 1e9),
-            "pdl": not a.no_pdl, "accumulate": "fp16 chains of 8 -> fp32",
+            "pdl": not a.no_pdl, "l2_prefetch_next_linear": a.l2_prefetch, "accumulate": "fp16 chains of 8 -> fp32",
         },
         "clocks": sampler.result(),
         "e2e": {"value": a.steps / dt_e2e if dt_e2e > 0 else None, "unit": UNIT, "h2d_bytes_per_step": d * 2,

@@ -25,7 +25,7 @@ NVCC_FLAGS = [
 
 EXPORTS = (
     "apg_version", "apg_status_string", "apg_last_cuda_error", "apg_gemv", "apg_gemv_ex", "apg_dequant",
-    "apg_round_f32_to_f16",
+    "apg_round_f32_to_f16", "apg_prefetch_hint",
 )
 
 
@@ -82,6 +82,8 @@ def lib() -> ctypes.CDLL:
     L.apg_gemv_ex.argtypes = [vp, vp, vp, vp, vp, u32, u32, u32, i32, u32, i32, vp]
     L.apg_dequant.restype = i32
     L.apg_dequant.argtypes = [vp, vp, vp, u32, u32, i32, vp]
+    L.apg_prefetch_hint.restype = i32
+    L.apg_prefetch_hint.argtypes = [vp, ctypes.c_uint64]
     L.apg_round_f32_to_f16.restype = i32
     L.apg_round_f32_to_f16.argtypes = [vp, vp, u32, vp]
     _lib = L

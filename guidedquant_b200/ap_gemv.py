@@ -57,8 +57,13 @@ def _check_gemv_args(input, output, qweight, lut, bitwidth):
     return input.size(0), N, K
 
 
-def anyprec_gemv_ex(input, output, qweight, lut, bitwidth, flags: int = 0, partial=None, ctas_per_sm: int = 0) -> None:
+def anyprec_gemv_ex(input, output, qweight, lut, bitwidth, flags: int = 0, partial=None, ctas_per_sm: int = 0,
+                    prefetch_next: torch.Tensor | None = None) -> None:
+    """anyprec_gemv with the C-ABI's options; `prefetch_next` = the packed weights the NEXT launch on this stream will
+    read (L2 prefetch hint, performance only)."""
     M, N, K = _check_gemv_args(input, output, qweight, lut, bitwidth)
+    if prefetch_next is not None:
+        _lib.lib().apg_prefetch_hint(prefetch_next.data_ptr(), prefetch_next.numel() * prefetch_next.element_size())
     if partial is not None:
         _req(partial.dtype == torch.float32 and partial.is_contiguous() and partial.numel() == M * N
              and partial.device == input.device, "partial must be a contiguous float32 [M, N] tensor on the same GPU.")

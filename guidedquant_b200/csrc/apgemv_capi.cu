@@ -12,6 +12,8 @@
 namespace {
 
 thread_local int g_last_cuda_error = 0;
+thread_local const void *g_prefetch_ptr = nullptr;  // one-shot hint consumed by the next fast GEMV launch
+thread_local uint64_t g_prefetch_bytes = 0;
 
 inline int cuda_fail(cudaError_t e) {
     g_last_cuda_error = (int)e;
@@ -47,7 +49,7 @@ inline bool aligned(const void *p, uintptr_t a) { return (reinterpret_cast<uintp
 constexpr size_t kFastMaxSmem = 200 * 1024;
 
 struct FastPlan {
-    uint32_t cpw, nwk, groups, rs, nslots, stage_bytes, grid, rows_per_cta, threads;
+    uint32_t cpw, nwk, groups, rs, nslots, stage_bytes, grid, rows_per_cta, threads, tot_stages;
     size_t smem;
 };
 
@@ -73,6 +75,7 @@ bool plan_fast(uint32_t N, uint32_t K, int ctas_per_sm, int sms, FastPlan *pl) {
     if (grid < 1) grid = 1;
     pl->grid = grid;
     const uint32_t tot_stages = (N + rs - 1) / rs;
+    pl->tot_stages = tot_stages;
     const uint32_t stages_per_cta = (tot_stages + grid - 1) / grid;
     pl->rows_per_cta = stages_per_cta * rs;
     // ring: as deep as the CTA's share needs, bounded so that c CTAs (+ a dependent kernel's) fit in 227 KB
@@ -116,7 +119,8 @@ int launch_fast_inst(const apg::FastParams &p, const FastPlan &pl, uint32_t flag
 
 template <int BITS>
 int launch_fast(const void *x, void *out, float *partial, const void *qweight, const void *lut, uint32_t N,
-                uint32_t K, uint32_t flags, int ctas_per_sm, cudaStream_t stream, DevInfo *dev) {
+                uint32_t K, uint32_t flags, int ctas_per_sm, cudaStream_t stream, DevInfo *dev,
+                const void *prefetch, uint64_t prefetch_bytes) {
     FastPlan pl;
     if (!plan_fast<BITS>(N, K, ctas_per_sm, dev->sms, &pl)) return APG_ERR_UNSUPPORTED;
     apg::FastParams p;
@@ -131,6 +135,11 @@ int launch_fast(const void *x, void *out, float *partial, const void *qweight, c
     p.groups = pl.groups;
     p.nslots = pl.nslots;
     p.stage_bytes = pl.stage_bytes;
+    p.stages_q = pl.tot_stages / pl.grid;
+    p.stages_rem = pl.tot_stages % pl.grid;
+    p.inv_nwk = (65536u + pl.nwk - 1) / pl.nwk;
+    p.prefetch = static_cast<const uint8_t *>(prefetch);
+    p.prefetch_bytes = (prefetch && aligned(prefetch, 16)) ? prefetch_bytes : 0;
 #define APG_FAST_CASE(CPW_, RS_) \
     if (pl.cpw == CPW_ && pl.rs == RS_) return launch_fast_inst<BITS, CPW_, RS_>(p, pl, flags, stream);
     APG_FAST_CASE(1, 8)
@@ -185,10 +194,13 @@ int apg_gemv_ex(const void *x, void *out, float *partial_f32, const void *qweigh
 
     const bool fast_ok = M == 1 && bits <= 4 && (K % 128u) == 0 && K <= 32768u && aligned(qweight, 16) &&
                          aligned(lut, 16) && !(flags & (APG_FLAG_REF_ORDER | APG_FLAG_GENERIC));
+    const void *pf = g_prefetch_ptr;
+    const uint64_t pfb = g_prefetch_bytes;
+    g_prefetch_ptr = nullptr, g_prefetch_bytes = 0;
     if (fast_ok) {
-        if (bits == 2) rc = launch_fast<2>(x, out, partial_f32, qweight, lut, N, K, flags, ctas_per_sm, stream, dev);
-        if (bits == 3) rc = launch_fast<3>(x, out, partial_f32, qweight, lut, N, K, flags, ctas_per_sm, stream, dev);
-        if (bits == 4) rc = launch_fast<4>(x, out, partial_f32, qweight, lut, N, K, flags, ctas_per_sm, stream, dev);
+        if (bits == 2) rc = launch_fast<2>(x, out, partial_f32, qweight, lut, N, K, flags, ctas_per_sm, stream, dev, pf, pfb);
+        if (bits == 3) rc = launch_fast<3>(x, out, partial_f32, qweight, lut, N, K, flags, ctas_per_sm, stream, dev, pf, pfb);
+        if (bits == 4) rc = launch_fast<4>(x, out, partial_f32, qweight, lut, N, K, flags, ctas_per_sm, stream, dev, pf, pfb);
         if (rc != APG_ERR_UNSUPPORTED) return rc;
     }
     const dim3 block(128), grid((N + 3) / 4);
@@ -201,6 +213,12 @@ int apg_gemv_ex(const void *x, void *out, float *partial_f32, const void *qweigh
             static_cast<const __half *>(x), static_cast<const uint32_t *>(qweight), static_cast<const __half *>(lut),
             static_cast<__half *>(out), partial_f32, M, N, K, bits);
     APG_CUDA(cudaGetLastError());
+    return APG_OK;
+}
+
+int apg_prefetch_hint(const void *next_weights, uint64_t bytes) {
+    g_prefetch_ptr = next_weights;
+    g_prefetch_bytes = next_weights ? bytes : 0;
     return APG_OK;
 }
 

@@ -387,6 +387,10 @@ struct FastParams {
     uint32_t groups;         // row groups per CTA; consumer warps = groups * nwk; +1 producer warp
     uint32_t nslots;         // ring slots (multiple of groups)
     uint32_t stage_bytes;    // RS * BITS * K/8
+    uint32_t stages_q, stages_rem;  // stages per CTA: CTA b owns stages_q + (b < stages_rem) consecutive stages
+    uint32_t inv_nwk;        // ceil(65536 / nwk): warp / nwk == (warp * inv_nwk) >> 16 for warp < 64
+    const uint8_t *prefetch; // optional: bytes the NEXT kernel on the stream will stream (its weights) ...
+    uint64_t prefetch_bytes; // ... pulled into L2 by this kernel's producer threads while its warps compute
 };
 
 // smem: [barriers 2*nslots*8 | pad->256 | tables (per consumer warp) | ring nslots*stage_bytes | red floats]
@@ -409,10 +413,9 @@ __global__ void __launch_bounds__(544, 1) gemv_fast_kernel(const FastParams p) {
     float *red = reinterpret_cast<float *>(smem_raw + (ring0 - smem0) + NS * p.stage_bytes);
 
     // rows of this CTA: whole stages of RS rows (only the matrix's last stage can be partial)
-    const uint32_t tot_stages = (N + RS - 1) / RS;
-    const uint32_t s_begin = (uint32_t)(((uint64_t)tot_stages * blockIdx.x) / gridDim.x);
-    const uint32_t s_end = (uint32_t)(((uint64_t)tot_stages * (blockIdx.x + 1)) / gridDim.x);
-    const uint32_t nstages = s_end - s_begin;
+    const uint32_t s_begin = blockIdx.x * p.stages_q + min(blockIdx.x, p.stages_rem);
+    const uint32_t nstages = p.stages_q + (blockIdx.x < p.stages_rem ? 1u : 0u);
+    const uint32_t s_end = s_begin + nstages;
     const uint32_t r_begin = s_begin * RS;
     const uint32_t r_end = min(s_end * RS, N);
     const uint32_t nrows = r_end - r_begin;
@@ -430,8 +433,27 @@ __global__ void __launch_bounds__(544, 1) gemv_fast_kernel(const FastParams p) {
         // ===================== producer: stream [r_begin, r_end) through the ring =====================
         if (lane == 0) {
             const uint64_t pol = l2_policy_evict_first();
+            // L2 prefetch of what the next kernel on the stream will read (its packed weights): HBM is mostly idle
+            // while this kernel's warps chew through their tables, and the successor's ring then fills at L2 latency.
+            // Issued once, right after this CTA's own ring has been filled for the first time.
+            auto prefetch_next = [&]() {
+                if (!p.prefetch_bytes) return;
+                const uint64_t per = ((p.prefetch_bytes / gridDim.x) + 15u) & ~15ull;
+                const uint64_t off = per * blockIdx.x;
+                if (off >= p.prefetch_bytes) return;
+                uint64_t n = min(per, p.prefetch_bytes - off) & ~15ull;
+                const uint8_t *src = p.prefetch + off;
+                while (n) {
+                    const uint32_t c = (uint32_t)min(n, (uint64_t)65536u);
+                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(c) : "memory");
+                    src += c, n -= c;
+                }
+            };
+            const uint32_t pf_at = min(NS, nstages);
             uint32_t slot = 0, use = 0;
+            if (pf_at == 0) prefetch_next();
             for (uint32_t s = 0; s < nstages; s++) {
+                if (s == pf_at) prefetch_next();
                 if (use > 0) mbar_wait_backoff(bar_empty + 8u * slot, (use - 1u) & 1u);
                 const uint32_t row0 = r_begin + s * RS;
                 const uint32_t rows = min((uint32_t)RS, r_end - row0);
@@ -443,10 +465,11 @@ __global__ void __launch_bounds__(544, 1) gemv_fast_kernel(const FastParams p) {
                              p.W + ((size_t)j * N + row0) * row_bytes, bytes, bar_full + 8u * slot, pol);
                 if (++slot == NS) slot = 0, use++;
             }
+            if (pf_at == nstages && nstages > 0) prefetch_next();
         }
     } else {
         // ===================== consumers =====================
-        const uint32_t g = warp / nwk, wk = warp - g * nwk;
+        const uint32_t g = ((uint32_t)warp * p.inv_nwk) >> 16, wk = warp - g * nwk;
         const uint32_t tbl = tbl0 + warp * WTB;
         const uint32_t nchunk = (K + 1023u) >> 10;
 

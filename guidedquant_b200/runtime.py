@@ -61,13 +61,15 @@ class _Lin:
 
 class ApGemvChain:
     def __init__(self, model: str = "llama3-8b", bits: int = 2, device=None, seed: int = 0, n_layer: int | None = None,
-                 pdl: bool = True, world_size: int = 1, rank: int = 0, process_group=None, ctas_per_sm: int = 0):
+                 pdl: bool = True, world_size: int = 1, rank: int = 0, process_group=None, ctas_per_sm: int = 0,
+                 l2_prefetch: bool = False):
         self.cfg = dict(MODEL_CONFIGS[model])
         if n_layer is not None:
             self.cfg["n_layer"] = n_layer
         self.model, self.bits, self.pdl = model, bits, pdl
         self.world, self.rank, self.pg = world_size, rank, process_group
         self.ctas = ctas_per_sm
+        self.l2_prefetch = l2_prefetch
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
         self.shapes = linear_shapes(self.cfg)
         self.layers: list[list[_Lin]] = []
@@ -127,19 +129,21 @@ class ApGemvChain:
         return sum(l.qweight.numel() * 4 + l.lut.numel() * 2 for lins in self.layers for l in lins)
 
     # ------------------------------------------------------------------ one token
-    def _gemv(self, lin: _Lin, x: torch.Tensor, out: torch.Tensor):
+    def _gemv(self, lin: _Lin, x: torch.Tensor, out: torch.Tensor, nxt: _Lin | None = None):
         flags = _lib.APG_FLAG_PDL if self.pdl else 0
         self.launches_per_step += 1
+        pf = nxt.qweight if (nxt is not None and self.l2_prefetch) else None
         if lin.k_shard:
             ap_gemv.anyprec_gemv_ex(x, out, lin.qweight, lin.lut, self.bits, flags=flags, partial=self.part,
-                                    ctas_per_sm=self.ctas)
+                                    ctas_per_sm=self.ctas, prefetch_next=pf)
             torch.distributed.all_reduce(self.part, group=self.pg)
             st = _lib.lib().apg_round_f32_to_f16(self.part.data_ptr(), out.data_ptr(), out.numel(),
                                                  torch.cuda.current_stream().cuda_stream)
             _lib.check(st, "apg_round_f32_to_f16")
             self.launches_per_step += 1
         else:
-            ap_gemv.anyprec_gemv_ex(x, out, lin.qweight, lin.lut, self.bits, flags=flags, ctas_per_sm=self.ctas)
+            ap_gemv.anyprec_gemv_ex(x, out, lin.qweight, lin.lut, self.bits, flags=flags, ctas_per_sm=self.ctas,
+                                    prefetch_next=pf)
 
     def _token(self):
         """the 4*L dependent GEMVs of one token.  Between Linears the (out-of-scope) attention / SwiGLU are
@@ -152,10 +156,11 @@ class ApGemvChain:
         for li, lins in enumerate(self.layers):
             wqkv, wo, w1w3, w2 = lins
             h_out = b["h"] if li % 2 == 0 else b["h2"]
-            self._gemv(wqkv, x, self._view(b["qkv"], 0, wqkv.N))
-            self._gemv(wo, self._view(b["qkv"], 0, wo.K), b["o"])
-            self._gemv(w1w3, b["o"], self._view(b["gu"], 0, w1w3.N))
-            self._gemv(w2, self._view(b["gu"], 0, w2.K), h_out)
+            nxt_wqkv = self.layers[li + 1][0] if li + 1 < len(self.layers) else self.layers[0][0]
+            self._gemv(wqkv, x, self._view(b["qkv"], 0, wqkv.N), wo)
+            self._gemv(wo, self._view(b["qkv"], 0, wo.K), b["o"], w1w3)
+            self._gemv(w1w3, b["o"], self._view(b["gu"], 0, w1w3.N), w2)
+            self._gemv(w2, self._view(b["gu"], 0, w2.K), h_out, nxt_wqkv)
             x = h_out
         self.y_dev = x
         return x

@@ -76,6 +76,14 @@ int apg_gemv_ex(const void *x, void *out, float *partial_f32, const void *qweigh
                 void *stream);
 
 /*
+ * Optional one-shot hint (per calling thread), consumed by the NEXT apg_gemv / apg_gemv_ex launch that takes the fast
+ * path: `next_weights[0, bytes)` (16-byte aligned; normally the qweight tensor of the Linear that follows on the
+ * stream) is pulled into L2 by that launch's producer threads while its warps compute.  Purely a performance hint:
+ * results never depend on it.  No reference counterpart (the reference issues one isolated launch per Linear).
+ */
+int apg_prefetch_hint(const void *next_weights, uint64_t bytes);
+
+/*
  * Replaces ap_gemv.anyprec_dequant(qweight, lut, bitwidth) -> fp16 [N, K]
  *   (inference/ap_gemv/gemv.cu:109-134 -> dequant_kbit_store, anyprec.cu:294-359, 622-645).
  * w_out[n, k] = lut[n, idx[n, k]] — a pure gather, bit-identical to the reference.
@@ -84,8 +92,7 @@ int apg_gemv_ex(const void *x, void *out, float *partial_f32, const void *qweigh
 int apg_dequant(const void *qweight, const void *lut, void *w_out,
                 uint32_t N, uint32_t K, int bits, void *stream);
 
-/* fp32 [n] -> fp16 [n] round-to-nearest-even, optionally adding an fp16 bias; the epilogue of the
- * K-sharded path after the fp32 all-reduce. */
+/* fp32 [n] -> fp16 [n] round-to-nearest-even; the epilogue of the K-sharded path after the fp32 all-reduce. */
 int apg_round_f32_to_f16(const float *in, void *out, uint32_t n, void *stream);
 
 #ifdef __cplusplus
