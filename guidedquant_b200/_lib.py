@@ -25,7 +25,8 @@ NVCC_FLAGS = [
 
 EXPORTS = (
     "apg_version", "apg_status_string", "apg_last_cuda_error", "apg_gemv", "apg_gemv_ex", "apg_dequant",
-    "apg_round_f32_to_f16", "apg_prefetch_hint",
+    "apg_round_f32_to_f16", "apg_prefetch_hint", "apg_gemv_fused",
+    "apd_embed", "apd_attn_decode", "apd_lm_head", "apd_argmax_advance",
 )
 
 
@@ -82,6 +83,17 @@ def lib() -> ctypes.CDLL:
     L.apg_gemv_ex.argtypes = [vp, vp, vp, vp, vp, u32, u32, u32, i32, u32, i32, vp]
     L.apg_dequant.restype = i32
     L.apg_dequant.argtypes = [vp, vp, vp, u32, u32, i32, vp]
+    L.apg_gemv_fused.restype = i32
+    L.apg_gemv_fused.argtypes = [vp, vp, vp, vp, vp, u32, u32, i32, vp, ctypes.c_float, i32, vp, u32, vp]
+    f32 = ctypes.c_float
+    L.apd_embed.restype = i32
+    L.apd_embed.argtypes = [vp, vp, vp, u32, u32, vp]
+    L.apd_attn_decode.restype = i32
+    L.apd_attn_decode.argtypes = [vp, vp, vp, vp, vp, vp, vp, u32, u32, u32, u32, f32, u32, vp]
+    L.apd_lm_head.restype = i32
+    L.apd_lm_head.argtypes = [vp, vp, f32, vp, vp, u32, u32, u32, vp]
+    L.apd_argmax_advance.restype = i32
+    L.apd_argmax_advance.argtypes = [vp, u32, vp, vp, vp, u32, u32, vp]
     L.apg_prefetch_hint.restype = i32
     L.apg_prefetch_hint.argtypes = [vp, ctypes.c_uint64]
     L.apg_round_f32_to_f16.restype = i32

@@ -40,7 +40,9 @@ def _check_gemv_args(input, output, qweight, lut, bitwidth):
     N, K = output.size(2), input.size(2)
     _req(lut.dim() == 2 and lut.size(1) == (1 << bitwidth) and lut.size(0) == N,
          f"lut tensor must be of shape (output_feat, 2 ** bitwidth). Expected ({N}, {1 << bitwidth}), got {tuple(lut.shape)}.")
-    _req(qweight.dim() == 3 and qweight.size(0) == bitwidth and qweight.size(2) == K // 32 and qweight.size(1) == N,
+    # the reference requires qweight.size(0) == bitwidth (gemv.cu:76); a multi-precision tensor with MORE planes is
+    # accepted here and its first `bitwidth` planes are used (plane-major layout, any-precision property)
+    _req(qweight.dim() == 3 and qweight.size(0) >= bitwidth and qweight.size(2) == K // 32 and qweight.size(1) == N,
          f"qweight tensor must be of shape (bitwidth, output_feat, input_feat / 32). Expected ({bitwidth}, {N}, {K // 32}), got {tuple(qweight.shape)}.")
     _req(input.size(1) == 1, "Only sequence length of 1 is supported.")
     _req(output.size(1) == 1, "Only sequence length of 1 is supported.")

@@ -12,6 +12,12 @@
 namespace {
 
 thread_local int g_last_cuda_error = 0;
+struct Fusion {
+    const void *norm_w = nullptr;
+    float eps = 0.f;
+    int silu_mul = 0;
+    const void *residual = nullptr;
+};
 thread_local const void *g_prefetch_ptr = nullptr;  // one-shot hint consumed by the next fast GEMV launch
 thread_local uint64_t g_prefetch_bytes = 0;
 
@@ -86,7 +92,7 @@ bool plan_fast(uint32_t N, uint32_t K, int ctas_per_sm, int sms, FastPlan *pl) {
     if (ns < pl->groups) ns = pl->groups;
     pl->nslots = ns;
     const uint32_t wtb = rs == 8 ? apg::FastWarpTbl<BITS, 8>::BYTES : (rs == 4 ? apg::FastWarpTbl<BITS, 4>::BYTES : apg::FastWarpTbl<BITS, 2>::BYTES);
-    pl->smem = 2 * (size_t)ns * 8 + 256 + (size_t)ncons * wtb + (size_t)ns * pl->stage_bytes +
+    pl->smem = 2 * (size_t)ns * 8 + 512 + (size_t)ncons * wtb + (size_t)ns * pl->stage_bytes +
                (size_t)pl->rows_per_cta * pl->nwk * sizeof(float) + 16;
     return pl->smem <= kFastMaxSmem;
 }
@@ -120,7 +126,7 @@ int launch_fast_inst(const apg::FastParams &p, const FastPlan &pl, uint32_t flag
 template <int BITS>
 int launch_fast(const void *x, void *out, float *partial, const void *qweight, const void *lut, uint32_t N,
                 uint32_t K, uint32_t flags, int ctas_per_sm, cudaStream_t stream, DevInfo *dev,
-                const void *prefetch, uint64_t prefetch_bytes) {
+                const void *prefetch, uint64_t prefetch_bytes, const Fusion &fu) {
     FastPlan pl;
     if (!plan_fast<BITS>(N, K, ctas_per_sm, dev->sms, &pl)) return APG_ERR_UNSUPPORTED;
     apg::FastParams p;
@@ -138,6 +144,10 @@ int launch_fast(const void *x, void *out, float *partial, const void *qweight, c
     p.stages_q = pl.tot_stages / pl.grid;
     p.stages_rem = pl.tot_stages % pl.grid;
     p.inv_nwk = (65536u + pl.nwk - 1) / pl.nwk;
+    p.norm_w = static_cast<const __half *>(fu.norm_w);
+    p.norm_eps = fu.eps;
+    p.act_silu_mul = fu.silu_mul ? 1u : 0u;
+    p.residual = static_cast<const __half *>(fu.residual);
     p.prefetch = static_cast<const uint8_t *>(prefetch);
     p.prefetch_bytes = (prefetch && aligned(prefetch, 16)) ? prefetch_bytes : 0;
 #define APG_FAST_CASE(CPW_, RS_) \
@@ -175,8 +185,9 @@ const char *apg_status_string(int status) {
 
 int apg_last_cuda_error(void) { return g_last_cuda_error; }
 
-int apg_gemv_ex(const void *x, void *out, float *partial_f32, const void *qweight, const void *lut, uint32_t M,
-                uint32_t N, uint32_t K, int bits, uint32_t flags, int ctas_per_sm, void *stream_) {
+static int gemv_impl(const void *x, void *out, float *partial_f32, const void *qweight, const void *lut, uint32_t M,
+                     uint32_t N, uint32_t K, int bits, uint32_t flags, int ctas_per_sm, void *stream_, const Fusion &fu,
+                     bool fused) {
     using namespace apg;
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (!x || !qweight || !lut || (!out && !partial_f32)) return APG_ERR_NULL;
@@ -185,7 +196,8 @@ int apg_gemv_ex(const void *x, void *out, float *partial_f32, const void *qweigh
     if (N < 1 || K < 32 || (K % 32u) != 0) return APG_ERR_SHAPE;
     if (flags & ~(APG_FLAG_REF_ORDER | APG_FLAG_GENERIC | APG_FLAG_PDL)) return APG_ERR_MODE;
     if (!aligned(x, 16) || !aligned(qweight, 4) || !aligned(lut, 2) || (out && !aligned(out, 2)) ||
-        (partial_f32 && !aligned(partial_f32, 4)))
+        (partial_f32 && !aligned(partial_f32, 4)) || (fu.norm_w && !aligned(fu.norm_w, 16)) ||
+        (fu.residual && !aligned(fu.residual, 2)))
         return APG_ERR_ALIGN;
 
     DevInfo *dev = nullptr;
@@ -198,11 +210,12 @@ int apg_gemv_ex(const void *x, void *out, float *partial_f32, const void *qweigh
     const uint64_t pfb = g_prefetch_bytes;
     g_prefetch_ptr = nullptr, g_prefetch_bytes = 0;
     if (fast_ok) {
-        if (bits == 2) rc = launch_fast<2>(x, out, partial_f32, qweight, lut, N, K, flags, ctas_per_sm, stream, dev, pf, pfb);
-        if (bits == 3) rc = launch_fast<3>(x, out, partial_f32, qweight, lut, N, K, flags, ctas_per_sm, stream, dev, pf, pfb);
-        if (bits == 4) rc = launch_fast<4>(x, out, partial_f32, qweight, lut, N, K, flags, ctas_per_sm, stream, dev, pf, pfb);
+        if (bits == 2) rc = launch_fast<2>(x, out, partial_f32, qweight, lut, N, K, flags, ctas_per_sm, stream, dev, pf, pfb, fu);
+        if (bits == 3) rc = launch_fast<3>(x, out, partial_f32, qweight, lut, N, K, flags, ctas_per_sm, stream, dev, pf, pfb, fu);
+        if (bits == 4) rc = launch_fast<4>(x, out, partial_f32, qweight, lut, N, K, flags, ctas_per_sm, stream, dev, pf, pfb, fu);
         if (rc != APG_ERR_UNSUPPORTED) return rc;
     }
+    if (fused) return APG_ERR_UNSUPPORTED;  // the fused prologue/epilogue exists in the fast kernel only
     const dim3 block(128), grid((N + 3) / 4);
     if (flags & APG_FLAG_REF_ORDER)
         gemv_generic_kernel<true><<<grid, block, 0, stream>>>(
@@ -214,6 +227,19 @@ int apg_gemv_ex(const void *x, void *out, float *partial_f32, const void *qweigh
             static_cast<__half *>(out), partial_f32, M, N, K, bits);
     APG_CUDA(cudaGetLastError());
     return APG_OK;
+}
+
+int apg_gemv_ex(const void *x, void *out, float *partial_f32, const void *qweight, const void *lut, uint32_t M,
+                uint32_t N, uint32_t K, int bits, uint32_t flags, int ctas_per_sm, void *stream) {
+    return gemv_impl(x, out, partial_f32, qweight, lut, M, N, K, bits, flags, ctas_per_sm, stream, Fusion(), false);
+}
+
+int apg_gemv_fused(const void *x, void *out, float *partial_f32, const void *qweight, const void *lut, uint32_t N,
+                   uint32_t K, int bits, const void *norm_w, float norm_eps, int silu_mul, const void *residual,
+                   uint32_t flags, void *stream) {
+    Fusion fu;
+    fu.norm_w = norm_w, fu.eps = norm_eps, fu.silu_mul = silu_mul, fu.residual = residual;
+    return gemv_impl(x, out, partial_f32, qweight, lut, 1, N, K, bits, flags, 0, stream, fu, true);
 }
 
 int apg_prefetch_hint(const void *next_weights, uint64_t bytes) {

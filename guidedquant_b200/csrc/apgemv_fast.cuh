@@ -389,6 +389,11 @@ struct FastParams {
     uint32_t stage_bytes;    // RS * BITS * K/8
     uint32_t stages_q, stages_rem;  // stages per CTA: CTA b owns stages_q + (b < stages_rem) consecutive stages
     uint32_t inv_nwk;        // ceil(65536 / nwk): warp / nwk == (warp * inv_nwk) >> 16 for warp < 64
+    // ---- optional fusions of the ops that surround the Linear in the decode step (inference/model.py) ----
+    const __half *norm_w;    // != nullptr: x := RMSNorm(x) * norm_w before the GEMV (model.py:280-285), eps below
+    float norm_eps;
+    uint32_t act_silu_mul;   // 1: x := silu(x[0:K]) * x[K:2K] (FeedForward, model.py:261-266); x holds 2K halfs
+    const __half *residual;  // != nullptr: out := fp16(y) + residual in fp16 (TransformerBlock, model.py:151-167)
     const uint8_t *prefetch; // optional: bytes the NEXT kernel on the stream will stream (its weights) ...
     uint64_t prefetch_bytes; // ... pulled into L2 by this kernel's producer threads while its warps compute
 };
@@ -408,7 +413,8 @@ __global__ void __launch_bounds__(544, 1) gemv_fast_kernel(const FastParams p) {
 
     const uint32_t smem0 = smem_u32(smem_raw);
     const uint32_t bar_full = smem0, bar_empty = smem0 + NS * 8u;
-    const uint32_t tbl0 = (smem0 + 2u * NS * 8u + 255u) & ~255u;
+    float *ssq = reinterpret_cast<float *>(smem_raw + 2u * NS * 8u);  // [ncons] sums of squares (fused RMSNorm)
+    const uint32_t tbl0 = (smem0 + 2u * NS * 8u + 64u * 4u + 255u) & ~255u;
     const uint32_t ring0 = tbl0 + ncons * WTB;
     float *red = reinterpret_cast<float *>(smem_raw + (ring0 - smem0) + NS * p.stage_bytes);
 
@@ -482,6 +488,7 @@ __global__ void __launch_bounds__(544, 1) gemv_fast_kernel(const FastParams p) {
         uint32_t xr[CPW][16];
         bool act[CPW];
         uint32_t woff[CPW];  // byte offset of this lane's word inside a (row, plane)
+        float ss = 0.f;
 #pragma unroll
         for (int cc = 0; cc < CPW; cc++) {
             const uint32_t i = wk * CPW + cc;
@@ -491,8 +498,58 @@ __global__ void __launch_bounds__(544, 1) gemv_fast_kernel(const FastParams p) {
             if (act[cc]) {
 #pragma unroll
                 for (int c = 0; c < 4; c++) {
-                    const uint4 v = __ldg(reinterpret_cast<const uint4 *>(p.x + i * 1024u + c * 8u * eff + 8u * lane));
+                    const uint32_t k0 = i * 1024u + c * 8u * eff + 8u * lane;
+                    const uint4 v = __ldg(reinterpret_cast<const uint4 *>(p.x + k0));
                     xr[cc][4 * c + 0] = v.x, xr[cc][4 * c + 1] = v.y, xr[cc][4 * c + 2] = v.z, xr[cc][4 * c + 3] = v.w;
+                    if (p.act_silu_mul) {  // x := silu(gate) * up, both rounded to fp16 like the reference's half tensors
+                        const uint4 u = __ldg(reinterpret_cast<const uint4 *>(p.x + K + k0));
+                        const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                        for (int e = 0; e < 4; e++) {
+                            const float2 gf = __half22float2(*reinterpret_cast<const __half2 *>(&xr[cc][4 * c + e]));
+                            const __half2 sg = __floats2half2_rn(gf.x / (1.f + __expf(-gf.x)), gf.y / (1.f + __expf(-gf.y)));
+                            const __half2 r = __hmul2(sg, *reinterpret_cast<const __half2 *>(&uu[e]));
+                            xr[cc][4 * c + e] = *reinterpret_cast<const uint32_t *>(&r);
+                        }
+                    }
+                    if (p.norm_w) {
+#pragma unroll
+                        for (int e = 0; e < 4; e++) {
+                            const float2 f = __half22float2(*reinterpret_cast<const __half2 *>(&xr[cc][4 * c + e]));
+                            ss = fmaf(f.x, f.x, ss);
+                            ss = fmaf(f.y, f.y, ss);
+                        }
+                    }
+                }
+            }
+        }
+        if (p.norm_w) {
+            // fused RMSNorm (model.py:280-285): every row group covers all K chunks once, so the group's warps
+            // exchange their sums of squares through shared memory (fixed summation order)
+#pragma unroll
+            for (int o = 16; o >= 1; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+            if (lane == 0) ssq[warp] = ss;
+            asm volatile("bar.sync 1, %0;" ::"r"(ncons * 32u) : "memory");
+            float tot = 0.f;
+            for (uint32_t w = 0; w < nwk; w++) tot += ssq[g * nwk + w];
+            const float rs = rsqrtf(tot / (float)K + p.norm_eps);
+#pragma unroll
+            for (int cc = 0; cc < CPW; cc++) {
+                if (act[cc]) {
+                    const uint32_t i = wk * CPW + cc;
+                    const uint32_t eff = chunk_eff(K, i);
+#pragma unroll
+                    for (int c = 0; c < 4; c++) {
+                        const uint4 wv = __ldg(reinterpret_cast<const uint4 *>(p.norm_w + i * 1024u + c * 8u * eff + 8u * lane));
+                        const uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+                        for (int e = 0; e < 4; e++) {
+                            const float2 f = __half22float2(*reinterpret_cast<const __half2 *>(&xr[cc][4 * c + e]));
+                            const __half2 n = __floats2half2_rn(f.x * rs, f.y * rs);  // .type_as(x)
+                            const __half2 r = __hmul2(n, *reinterpret_cast<const __half2 *>(&ww[e]));  // * weight
+                            xr[cc][4 * c + e] = *reinterpret_cast<const uint32_t *>(&r);
+                        }
+                    }
                 }
             }
         }
@@ -534,7 +591,11 @@ __global__ void __launch_bounds__(544, 1) gemv_fast_kernel(const FastParams p) {
     for (uint32_t r = threadIdx.x; r < nrows; r += blockDim.x) {
         float v = red[r * nwk];
         for (uint32_t w = 1; w < nwk; w++) v += red[r * nwk + w];
-        if (p.out) p.out[r_begin + r] = __float2half_rn(v);
+        if (p.out) {
+            __half h = __float2half_rn(v);
+            if (p.residual) h = __hadd(h, p.residual[r_begin + r]);
+            p.out[r_begin + r] = h;
+        }
         if (p.partial) p.partial[r_begin + r] = v;
     }
 }
@@ -542,7 +603,7 @@ __global__ void __launch_bounds__(544, 1) gemv_fast_kernel(const FastParams p) {
 template <int BITS, int RS>
 inline size_t fast_smem_bytes(uint32_t ncons, uint32_t nslots, uint32_t stage_bytes, uint32_t rows_per_cta,
                               uint32_t nwk) {
-    return 2 * (size_t)nslots * 8 + 256 + (size_t)ncons * FastWarpTbl<BITS, RS>::BYTES + (size_t)nslots * stage_bytes +
+    return 2 * (size_t)nslots * 8 + 512 + (size_t)ncons * FastWarpTbl<BITS, RS>::BYTES + (size_t)nslots * stage_bytes +
            (size_t)rows_per_cta * nwk * sizeof(float) + 16;
 }
 

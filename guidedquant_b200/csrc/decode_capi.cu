@@ -1,0 +1,90 @@
+// C-ABI of the decode-step kernels (include/apdecode_b200.h): validation + launch only.
+#include "apdecode_b200.h"
+
+#include <cuda_runtime.h>
+
+#include "apgemv_b200.h"
+#include "decode_kernels.cuh"
+
+namespace {
+template <typename... KArgs, typename... Args>
+int launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, uint32_t flags, void *stream, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = static_cast<cudaStream_t>(stream);
+    cudaLaunchAttribute attr[1];
+    if (flags & APG_FLAG_PDL) {
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+    }
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...) == cudaSuccess ? APG_OK : APG_ERR_CUDA;
+}
+inline bool al(const void *p, uintptr_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
+}  // namespace
+
+extern "C" {
+
+int apd_embed(const void *emb, const int *token, void *x, uint32_t dim, uint32_t flags, void *stream) {
+    if (!emb || !token || !x) return APG_ERR_NULL;
+    if (dim == 0 || dim % 8) return APG_ERR_SHAPE;
+    if (!al(emb, 16) || !al(x, 16)) return APG_ERR_ALIGN;
+    return launch(apd::embed_kernel, dim3(1), dim3(256), 0, flags, stream, static_cast<const __half *>(emb), token,
+                  static_cast<__half *>(x), dim);
+}
+
+int apd_attn_decode(const void *qkv, const float *inv_freq, void *k_cache, void *v_cache, const int *pos, void *out,
+                    float *part_ws, uint32_t H, uint32_t Hkv, uint32_t S, uint32_t nsplit, float scale, uint32_t flags,
+                    void *stream) {
+    if (!qkv || !inv_freq || !k_cache || !v_cache || !pos || !out) return APG_ERR_NULL;
+    if (H == 0 || Hkv == 0 || H % Hkv || H / Hkv > 8 || S == 0 || nsplit == 0) return APG_ERR_SHAPE;
+    if (nsplit > 1 && !part_ws) return APG_ERR_NULL;
+    if (!al(qkv, 8) || !al(k_cache, 8) || !al(v_cache, 8) || !al(out, 8) || (part_ws && !al(part_ws, 16))) return APG_ERR_ALIGN;
+    int rc = launch(apd::attn_decode_kernel, dim3(Hkv, nsplit), dim3(32 * (H / Hkv)), 0, flags, stream,
+                    static_cast<const __half *>(qkv), inv_freq, static_cast<__half *>(k_cache),
+                    static_cast<__half *>(v_cache), pos, static_cast<__half *>(out), part_ws, H, Hkv, S, scale);
+    if (rc != APG_OK || nsplit == 1) return rc;
+    return launch(apd::attn_merge_kernel, dim3(H), dim3(apd::kHeadDim), 0, flags, stream,
+                  static_cast<const float *>(part_ws), static_cast<__half *>(out), nsplit);
+}
+
+int apd_lm_head(const void *x, const void *norm_w, float eps, const void *W, void *logits, uint32_t V, uint32_t D,
+                uint32_t flags, void *stream) {
+    if (!x || !norm_w || !W || !logits) return APG_ERR_NULL;
+    if (V == 0 || D == 0 || D % 256 || D > 8192) return APG_ERR_SHAPE;
+    if (!al(W, 16) || !al(x, 2) || !al(norm_w, 2)) return APG_ERR_ALIGN;
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+        return APG_ERR_CUDA;
+    const uint32_t nv = D / 256;
+    uint32_t grid = (uint32_t)sms * 2u;
+    if (grid * 8u > V) grid = (V + 7) / 8;
+    const size_t smem = (size_t)D * sizeof(float);
+    auto go = [&](auto kern) {
+        return launch(kern, dim3(grid), dim3(256), smem, flags, stream, static_cast<const __half *>(x),
+                      static_cast<const __half *>(norm_w), eps, static_cast<const __half *>(W),
+                      static_cast<__half *>(logits), V, D);
+    };
+    switch (nv) {
+        case 1: return go(apd::lm_head_kernel<1>);
+        case 2: return go(apd::lm_head_kernel<2>);
+        case 4: return go(apd::lm_head_kernel<4>);
+        case 8: return go(apd::lm_head_kernel<8>);
+        case 16: return go(apd::lm_head_kernel<16>);
+        case 32: return go(apd::lm_head_kernel<32>);
+        default: return APG_ERR_UNSUPPORTED;
+    }
+}
+
+int apd_argmax_advance(const void *logits, uint32_t V, int *token, int *pos, int *history, uint32_t history_len,
+                       uint32_t flags, void *stream) {
+    if (!logits || !token || !pos) return APG_ERR_NULL;
+    if (V == 0) return APG_ERR_SHAPE;
+    return launch(apd::argmax_advance_kernel, dim3(1), dim3(1024), 0, flags, stream, static_cast<const __half *>(logits),
+                  V, token, pos, history, history_len);
+}
+
+}  // extern "C"

@@ -1,0 +1,201 @@
+"""Decode runtime: the reference's gpt-fast Transformer (inference/model.py) at batch 1 / sequence 1 on top of the
+native kernels, one CUDA graph per token.
+
+Per block 5 launches (the reference's eager graph has 11 ops + what Inductor fuses):
+    wqkv  = apg_gemv_fused(x,  norm=input_layernorm)                       model.py:152-153, 211
+    att   = apd_attn_decode(wqkv)          RoPE + KV append + attention     model.py:206-236
+    h     = apg_gemv_fused(att, residual=x)                       wo        model.py:152, 236
+    gu    = apg_gemv_fused(h,  norm=post_attention_layernorm)     w1w3      model.py:159, 261
+    x'    = apg_gemv_fused(gu, silu_mul, residual=h)              w2        model.py:165, 266
+plus embedding, lm_head (final RMSNorm fused) and greedy sampling (generate.py:55-73 at temperature 0) per token.
+The token id and the position live in device memory and are advanced by the sampling kernel, so `generate()`
+replays the same graph without any host round trip.
+
+State-dict names follow the reference's converted checkpoints (inference/sqllm_llama_convert_fuse.py:71-116):
+    tok_embeddings.weight, layers.{i}.attention.{wqkv,wo}.{qweight,lut}, layers.{i}.feed_forward.{w1w3,w2}.{qweight,lut},
+    layers.{i}.{input_layernorm,post_attention_layernorm}.weight, norm.weight, output.weight
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+
+from . import _lib
+from .runtime import MODEL_CONFIGS, gemv_algo_bytes, linear_shapes
+
+ROPE_BASE = {"llama3-8b": 500000.0, "llama3-70b": 500000.0, "llama2-7b": 10000.0, "llama2-70b": 10000.0, "tiny": 500000.0,
+             "golden-tiny": 500000.0, "tiny128": 500000.0}
+MODEL_CONFIGS.setdefault("golden-tiny", dict(dim=256, n_layer=2, n_head=2, n_kv=1, inter=512, vocab=256))
+MODEL_CONFIGS.setdefault("tiny128", dict(dim=1024, n_layer=2, n_head=8, n_kv=2, inter=2048, vocab=1024))
+
+
+class APTransformer:
+    def __init__(self, model: str = "llama3-8b", bits: int = 2, max_seq_len: int = 256, device=None, pdl: bool = True,
+                 norm_eps: float = 1e-5, n_layer: int | None = None, attn_splits: int | None = None):
+        self.cfg = dict(MODEL_CONFIGS[model])
+        if n_layer is not None:
+            self.cfg["n_layer"] = n_layer
+        c = self.cfg
+        assert c["dim"] // c["n_head"] == 128, "the attention kernel is specialised for head_dim 128"
+        self.model, self.bits, self.S, self.eps = model, bits, max_seq_len, norm_eps
+        self.flags = _lib.APG_FLAG_PDL if pdl else 0
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.rope_base = ROPE_BASE.get(model, 10000.0)
+        self.shapes = linear_shapes(c)
+        d, dev, f16 = c["dim"], self.device, torch.float16
+        self.nsplit = attn_splits if attn_splits is not None else max(1, min(32, max_seq_len // 512))
+        self.sd: dict[str, torch.Tensor] = {}
+        # activations / state
+        self.x = torch.zeros(d, dtype=f16, device=dev)
+        self.h = torch.zeros(d, dtype=f16, device=dev)
+        self.qkv = torch.zeros(self.shapes["wqkv"][0], dtype=f16, device=dev)
+        self.att = torch.zeros(d, dtype=f16, device=dev)
+        self.gu = torch.zeros(self.shapes["w1w3"][0], dtype=f16, device=dev)
+        self.logits = torch.zeros(c["vocab"], dtype=f16, device=dev)
+        self.token = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.pos = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.history = torch.zeros(max_seq_len + 1, dtype=torch.int32, device=dev)
+        hd = 128
+        self.inv_freq = (1.0 / (self.rope_base ** (torch.arange(0, hd, 2, dtype=torch.int64).float() / hd))).to(dev)
+        self.k_cache = [torch.zeros((c["n_kv"], max_seq_len, hd), dtype=f16, device=dev) for _ in range(c["n_layer"])]
+        self.v_cache = [torch.zeros((c["n_kv"], max_seq_len, hd), dtype=f16, device=dev) for _ in range(c["n_layer"])]
+        self.part = torch.zeros(c["n_head"] * self.nsplit * 132, dtype=torch.float32, device=dev) if self.nsplit > 1 else None
+        self.graph = None
+        self.stream = torch.cuda.Stream(device=dev)
+        self.tok_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+        self.launches_per_token = 0
+
+    # ------------------------------------------------------------------ weights
+    def random_init(self, seed: int = 0):
+        """synthetic packed weights of the right shapes (the reference's --random_init, generate.py:235,412)."""
+        c, dev, bits = self.cfg, self.device, self.bits
+        g = torch.Generator(device=dev).manual_seed(4321 + seed)
+        sd = self.sd
+        sd["tok_embeddings.weight"] = torch.randn((c["vocab"], c["dim"]), device=dev, generator=g).half()
+        for i in range(c["n_layer"]):
+            for mod, names in (("attention", ("wqkv", "wo")), ("feed_forward", ("w1w3", "w2"))):
+                for nm in names:
+                    N, K = self.shapes[nm]
+                    sd[f"layers.{i}.{mod}.{nm}.qweight"] = torch.randint(-2**31, 2**31 - 1, (bits, N, K // 32), dtype=torch.int32, device=dev, generator=g)
+                    sd[f"layers.{i}.{mod}.{nm}.lut"] = (torch.randn((N, 1 << bits), device=dev, generator=g) * (1.6 / math.sqrt(K))).half()
+            sd[f"layers.{i}.input_layernorm.weight"] = (1 + 0.1 * torch.randn(c["dim"], device=dev, generator=g)).half()
+            sd[f"layers.{i}.post_attention_layernorm.weight"] = (1 + 0.1 * torch.randn(c["dim"], device=dev, generator=g)).half()
+        sd["norm.weight"] = (1 + 0.1 * torch.randn(c["dim"], device=dev, generator=g)).half()
+        sd["output.weight"] = (torch.randn((c["vocab"], c["dim"]), device=dev, generator=g) / math.sqrt(c["dim"])).half()
+        return self
+
+    def load_state_dict(self, sd: dict):
+        for k, v in sd.items():
+            self.sd[k] = v.to(self.device).contiguous()
+        return self
+
+    # ------------------------------------------------------------------ accounting
+    def algo_bytes_per_token(self, pos: int = 0) -> dict:
+        c = self.cfg
+        gemv = c["n_layer"] * sum(gemv_algo_bytes(N, K, self.bits) for (N, K) in self.shapes.values())
+        lm_head = 2 * c["vocab"] * c["dim"]
+        kv = c["n_layer"] * 2 * c["n_kv"] * 128 * 2 * (pos + 1)
+        misc = c["n_layer"] * 2 * c["dim"] * 2 + 2 * c["dim"] + 2 * c["vocab"] * 2
+        return {"gemv": gemv, "lm_head": lm_head, "kv": kv, "misc": misc, "total": gemv + lm_head + kv + misc}
+
+    # ------------------------------------------------------------------ one token
+    def _fused(self, x, out, name, N, K, norm=None, silu_mul=0, residual=None):
+        L = _lib.lib()
+        q, lut = self.sd[name + ".qweight"], self.sd[name + ".lut"]
+        st = L.apg_gemv_fused(x.data_ptr(), out.data_ptr(), None, q.data_ptr(), lut.data_ptr(), N, K, self.bits,
+                              norm.data_ptr() if norm is not None else None, self.eps, silu_mul,
+                              residual.data_ptr() if residual is not None else None, self.flags,
+                              torch.cuda.current_stream().cuda_stream)
+        _lib.check(st, "apg_gemv_fused " + name)
+        self.launches_per_token += 1
+
+    def decode_step(self):
+        """embedding -> L blocks -> lm_head -> greedy sample; reads self.token / self.pos on the device and advances them."""
+        L, c, sd, fl = _lib.lib(), self.cfg, self.sd, self.flags
+        st = torch.cuda.current_stream().cuda_stream
+        self.launches_per_token = 0
+        _lib.check(L.apd_embed(sd["tok_embeddings.weight"].data_ptr(), self.token.data_ptr(), self.x.data_ptr(), c["dim"], fl, st), "apd_embed")
+        self.launches_per_token += 1
+        scale = 1.0 / math.sqrt(128.0)
+        for i in range(c["n_layer"]):
+            p = f"layers.{i}."
+            (nq, kq), (no, ko), (ng, kg), (n2, k2) = (self.shapes[n] for n in ("wqkv", "wo", "w1w3", "w2"))
+            self._fused(self.x, self.qkv, p + "attention.wqkv", nq, kq, norm=sd[p + "input_layernorm.weight"])
+            _lib.check(L.apd_attn_decode(self.qkv.data_ptr(), self.inv_freq.data_ptr(), self.k_cache[i].data_ptr(),
+                                         self.v_cache[i].data_ptr(), self.pos.data_ptr(), self.att.data_ptr(),
+                                         self.part.data_ptr() if self.part is not None else None, c["n_head"], c["n_kv"],
+                                         self.S, self.nsplit, scale, fl, st), "apd_attn_decode")
+            self.launches_per_token += 1 + (1 if self.nsplit > 1 else 0)
+            self._fused(self.att, self.h, p + "attention.wo", no, ko, residual=self.x)
+            self._fused(self.h, self.gu, p + "feed_forward.w1w3", ng, kg, norm=sd[p + "post_attention_layernorm.weight"])
+            self._fused(self.gu, self.x, p + "feed_forward.w2", n2, k2, silu_mul=1, residual=self.h)
+        _lib.check(L.apd_lm_head(self.x.data_ptr(), sd["norm.weight"].data_ptr(), self.eps, sd["output.weight"].data_ptr(),
+                                 self.logits.data_ptr(), c["vocab"], c["dim"], fl, st), "apd_lm_head")
+        _lib.check(L.apd_argmax_advance(self.logits.data_ptr(), c["vocab"], self.token.data_ptr(), self.pos.data_ptr(),
+                                        self.history.data_ptr(), self.history.numel(), fl, st), "apd_argmax_advance")
+        self.launches_per_token += 2
+
+    # ------------------------------------------------------------------ graph + generation
+    def capture(self):
+        with torch.cuda.device(self.device):
+            s = self.stream
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                saved = (self.token.clone(), self.pos.clone())
+                self.decode_step()  # warm-up (function attributes, lazy init); its side effects are undone below
+                s.synchronize()
+                self.graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self.graph, stream=s):
+                    self.decode_step()
+                self.token.copy_(saved[0])
+                self.pos.copy_(saved[1])
+                s.synchronize()
+            torch.cuda.current_stream().wait_stream(s)
+        return self
+
+    def reset(self, first_token: int = 1):
+        with torch.cuda.stream(self.stream):
+            self.token.fill_(first_token)
+            self.pos.zero_()
+            self.history.zero_()
+            self.history[0] = first_token
+        self.stream.synchronize()
+
+    def step(self):
+        if self.graph is None:
+            self.capture()
+        with torch.cuda.stream(self.stream):
+            self.graph.replay()
+
+    def step_host(self, token_host: torch.Tensor) -> int:
+        """end-to-end call for one token: pinned-host token id -> H2D -> graph -> D2H of the sampled token."""
+        if self.graph is None:
+            self.capture()
+        with torch.cuda.stream(self.stream):
+            self.token.copy_(token_host, non_blocking=True)
+            self.graph.replay()
+            self.tok_host.copy_(self.token, non_blocking=True)
+        self.stream.synchronize()
+        return int(self.tok_host[0])
+
+    @torch.no_grad()
+    def generate(self, prompt: list[int], max_new_tokens: int) -> list[int]:
+        """greedy generation (the reference's generate(), generate.py:146-186, with a sequential prefill: prompts are
+        BOS-only in the reference's benchmark protocol, generate.py:310-313)."""
+        assert len(prompt) >= 1 and len(prompt) + max_new_tokens <= self.S
+        self.reset(prompt[0])
+        for t in prompt[1:]:  # teacher-forced prefill, one token at a time
+            self.step()
+            with torch.cuda.stream(self.stream):
+                self.token.fill_(t)
+                self.history[int(self.pos_host())] = t
+        for _ in range(max_new_tokens):
+            self.step()
+        self.stream.synchronize()
+        n = len(prompt) + max_new_tokens
+        return self.history[:n].cpu().tolist()
+
+    def pos_host(self) -> int:
+        self.stream.synchronize()
+        return int(self.pos.cpu()[0])

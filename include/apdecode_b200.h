@@ -1,0 +1,38 @@
+/*
+ * apdecode_b200 — C-ABI of the decode-step kernels around the Any-Precision GEMV.
+ * Exported by the same library as apgemv_b200.h (libapgemv_b200.so).  They restate, at batch 1 / sequence 1, the
+ * non-Linear ops of the reference's gpt-fast model (inference/model.py) and its sampling (inference/generate.py);
+ * RMSNorm, SiLU*mul and the residual adds are NOT here — they are fused into apg_gemv_fused.
+ * All pointers are device pointers; `token` and `pos` live in device memory so one CUDA graph serves every token.
+ * flags: APG_FLAG_PDL (apgemv_b200.h) launches with programmatic dependent launch.  Returns apg_status codes.
+ */
+#ifndef APDECODE_B200_H
+#define APDECODE_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* x[0:dim] = emb[*token, :]            tok_embeddings, model.py:123.  dim % 8 == 0. */
+int apd_embed(const void *emb, const int *token, void *x, uint32_t dim, uint32_t flags, void *stream);
+
+/* RoPE(q,k) + KV-cache append at *pos + softmax(q.K^T/sqrt(128)).V over t <= *pos     Attention.forward, model.py:206-236
+ *   qkv fp16 [(H+2*Hkv)*128] (q|k|v, model.py:211); inv_freq fp32 [64]; k_cache/v_cache fp16 [Hkv, S, 128];
+ *   out fp16 [H*128]; part_ws fp32 [H*nsplit*132] (only when nsplit > 1).  head_dim = 128, H/Hkv <= 8. */
+int apd_attn_decode(const void *qkv, const float *inv_freq, void *k_cache, void *v_cache, const int *pos, void *out,
+                    float *part_ws, uint32_t H, uint32_t Hkv, uint32_t S, uint32_t nsplit, float scale, uint32_t flags,
+                    void *stream);
+
+/* logits[V] (fp16) = W[V,D] . (RMSNorm(x) * norm_w)      Transformer.forward tail, model.py:128-129.  D % 256 == 0, D <= 8192. */
+int apd_lm_head(const void *x, const void *norm_w, float eps, const void *W, void *logits, uint32_t V, uint32_t D,
+                uint32_t flags, void *stream);
+
+/* greedy sampling (generate.py:55-73 at temperature 0): *token = argmax(logits) (first index on ties);
+ * history[*pos + 1] = *token (if history != NULL and in range); *pos += 1. */
+int apd_argmax_advance(const void *logits, uint32_t V, int *token, int *pos, int *history, uint32_t history_len,
+                       uint32_t flags, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

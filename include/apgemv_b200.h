@@ -76,6 +76,18 @@ int apg_gemv_ex(const void *x, void *out, float *partial_f32, const void *qweigh
                 void *stream);
 
 /*
+ * M = 1 GEMV fused with the element-wise ops that surround a Linear in the reference's decode step
+ * (inference/model.py), so that a transformer block is 5 launches instead of 11:
+ *   norm_w   != NULL: x := (fp16)(x * rsqrt(mean(x^2) + norm_eps)) * norm_w       RMSNorm.forward, model.py:280-285
+ *   silu_mul != 0   : x := silu(x[0:K]) * x[K:2K]  (x holds 2K halfs)             FeedForward.forward, model.py:261-266
+ *   residual != NULL: out := (fp16)y + residual  (fp16 add)                       TransformerBlock.forward, model.py:151-167
+ * Fast-path shapes only (bits 2..4, K % 128 == 0, K <= 32768); otherwise APG_ERR_UNSUPPORTED.
+ */
+int apg_gemv_fused(const void *x, void *out, float *partial_f32, const void *qweight, const void *lut,
+                   uint32_t N, uint32_t K, int bits, const void *norm_w, float norm_eps, int silu_mul,
+                   const void *residual, uint32_t flags, void *stream);
+
+/*
  * Optional one-shot hint (per calling thread), consumed by the NEXT apg_gemv / apg_gemv_ex launch that takes the fast
  * path: `next_weights[0, bytes)` (16-byte aligned; normally the qweight tensor of the Linear that follows on the
  * stream) is pulled into L2 by that launch's producer threads while its warps compute.  Purely a performance hint:

@@ -1,0 +1,84 @@
+"""TEST INFRASTRUCTURE — NOT PRODUCT CODE.
+
+CPU restatement (torch, float32 arithmetic with explicit fp16 roundings) of ONE decode step of the reference's
+gpt-fast Transformer at batch 1 (inference/model.py: Transformer.forward :121-131, TransformerBlock.forward :151-167,
+Attention.forward :206-236, FeedForward.forward :259-266, RMSNorm :274-285, rotate_half / apply_rotary_pos_emb
+:268-272, :309-314, LlamaRotaryEmbedding.forward :381-405) and of greedy sampling (inference/generate.py:55-73 at
+temperature 0).  Linear layers take DENSE weights (for APLinear: the oracle's dequantised W, i.e. the
+"dequant -> fp16 matmul" semantics of APLinear.gemm, APLinear.py:35-38).
+
+Parity status: PINNED to the reference's own model.py run on CPU in float32 (tests/golden/make_decode_golden.py ->
+tests/golden/decode_golden.npz): with half_rounding=False this module reproduces those logits to float32 accuracy.
+half_rounding=True additionally rounds to fp16 wherever the reference holds fp16 tensors when the model is .half().
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+
+
+class DecodeOracle:
+    def __init__(self, weights: dict, n_layer: int, n_head: int, n_kv: int, dim: int, max_seq: int, rope_base: float,
+                 eps: float = 1e-5, half_rounding: bool = True):
+        """weights: name -> float tensor, names as in the reference's state dict:
+        tok_embeddings.weight, layers.{i}.attention.wqkv.weight / .wo.weight, layers.{i}.feed_forward.w1w3.weight /
+        .w2.weight, layers.{i}.input_layernorm.weight / .post_attention_layernorm.weight, norm.weight, output.weight"""
+        self.w = {k: v.float() for k, v in weights.items()}
+        self.L, self.H, self.Hkv, self.dim, self.S = n_layer, n_head, n_kv, dim, max_seq
+        self.hd = dim // n_head
+        self.eps, self.hr = eps, half_rounding
+        # default rope init: inv_freq = 1 / base^(arange(0, dim, 2) / dim), attention_scaling = 1
+        self.inv_freq = 1.0 / (rope_base ** (torch.arange(0, self.hd, 2, dtype=torch.int64).float() / self.hd))
+        self.k_cache = [torch.zeros(n_kv, max_seq, self.hd) for _ in range(n_layer)]
+        self.v_cache = [torch.zeros(n_kv, max_seq, self.hd) for _ in range(n_layer)]
+
+    def r(self, t: torch.Tensor) -> torch.Tensor:  # "this tensor is fp16 in the reference"
+        return t.half().float() if self.hr else t
+
+    def rmsnorm(self, x, w):  # model.py:280-285
+        n = x * torch.rsqrt(torch.mean(x * x, dim=-1, keepdim=True) + self.eps)
+        return self.r(self.r(n) * w)
+
+    def linear(self, x, W):  # fp16 GEMV with fp32 accumulation, fp16 output
+        return self.r(W @ x)
+
+    @staticmethod
+    def rotate_half(x):  # model.py:268-272
+        h = x.shape[-1] // 2
+        return torch.cat((-x[..., h:], x[..., :h]), dim=-1)
+
+    def step(self, token: int, pos: int) -> torch.Tensor:
+        """logits (float) for `token` at position `pos`; updates the KV caches."""
+        w, H, Hkv, hd = self.w, self.H, self.Hkv, self.hd
+        x = self.r(w["tok_embeddings.weight"][token])
+        freqs = self.inv_freq * float(pos)
+        emb = torch.cat((freqs, freqs))
+        cos, sin = self.r(emb.cos()), self.r(emb.sin())  # computed in fp32, cast to x.dtype (model.py:396-405)
+        for i in range(self.L):
+            p = f"layers.{i}."
+            xn = self.rmsnorm(x, w[p + "input_layernorm.weight"])
+            qkv = self.linear(xn, w[p + "attention.wqkv.weight"])
+            q = qkv[: H * hd].view(H, hd)
+            k = qkv[H * hd: (H + Hkv) * hd].view(Hkv, hd)
+            v = qkv[(H + Hkv) * hd:].view(Hkv, hd)
+            q = self.r(self.r(q * cos) + self.r(self.rotate_half(q) * sin))  # model.py:309-314
+            k = self.r(self.r(k * cos) + self.r(self.rotate_half(k) * sin))
+            self.k_cache[i][:, pos] = k
+            self.v_cache[i][:, pos] = v
+            kk = self.k_cache[i][:, : pos + 1].repeat_interleave(H // Hkv, dim=0)  # [H, T, hd] (model.py:229-230)
+            vv = self.v_cache[i][:, : pos + 1].repeat_interleave(H // Hkv, dim=0)
+            att = torch.softmax(torch.einsum("hd,htd->ht", q, kk) / math.sqrt(hd), dim=-1)  # SDPA, causal row
+            y = self.r(torch.einsum("ht,htd->hd", att, vv)).reshape(-1)
+            h = self.r(x + self.linear(y, w[p + "attention.wo.weight"]))  # model.py:152-155
+            hn = self.rmsnorm(h, w[p + "post_attention_layernorm.weight"])
+            gu = self.linear(hn, w[p + "feed_forward.w1w3.weight"])
+            inter = gu.numel() // 2
+            act = self.r(self.r(torch.nn.functional.silu(gu[:inter])) * gu[inter:])  # model.py:261-266
+            x = self.r(h + self.linear(act, w[p + "feed_forward.w2.weight"]))  # model.py:165
+        xn = self.rmsnorm(x, w["norm.weight"])
+        return self.linear(xn, w["output.weight"])
+
+    @staticmethod
+    def greedy(logits: torch.Tensor) -> int:  # generate.py:55-73 with temperature 0 == argmax
+        return int(torch.argmax(logits))

@@ -15,9 +15,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def test_capi_exports_every_declared_symbol():
     from guidedquant_b200 import _lib
 
-    hdr = open(os.path.join(ROOT, "include", "apgemv_b200.h")).read()
+    hdr = open(os.path.join(ROOT, "include", "apgemv_b200.h")).read() + open(os.path.join(ROOT, "include", "apdecode_b200.h")).read()
     hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
-    declared = set(re.findall(r"\b(apg_[a-z0-9_]+)\s*\(", hdr))
+    declared = set(re.findall(r"\b(ap[gd]_[a-z0-9_]+)\s*\(", hdr))
+    assert {"apd_embed", "apd_attn_decode", "apd_lm_head", "apd_argmax_advance", "apg_gemv_fused"} <= declared
     assert {"apg_gemv", "apg_gemv_ex", "apg_dequant", "apg_version"} <= declared
     path = _lib.build()
     L = ctypes.CDLL(path)

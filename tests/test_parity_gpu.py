@@ -184,3 +184,62 @@ def test_error_behaviour():
         ap_gemv.anyprec_gemv(x.bfloat16(), out.bfloat16(), q, lut.bfloat16(), 2)
     with pytest.raises(RuntimeError, match="type int"):
         ap_gemv.anyprec_gemv(x, out, q.long(), lut, 2)
+
+
+def test_any_precision_linear_module(oracle):
+    """HF-side module surface: one shared 4-plane qweight, lut3 / lut4, set_precision, prefill path == decode path."""
+    from guidedquant_b200.AnyPrecisionLinear import AnyPrecisionLinear
+
+    N, K = 96, 2048
+    rng = np.random.default_rng(9)
+    idx4 = rng.integers(0, 16, size=(N, K), dtype=np.uint8)
+    q4 = oracle.pack(idx4, 4)
+    lut4 = (rng.standard_normal((N, 16)) * 0.02).astype(np.float16)
+    lut3 = (rng.standard_normal((N, 8)) * 0.02).astype(np.float16)
+    m = AnyPrecisionLinear(K, N, [3, 4], bias=False, device="cuda", dtype=torch.float16)
+    m.qweight.copy_(torch.from_numpy(q4))
+    m.lut4.copy_(torch.from_numpy(lut4))
+    m.lut3.copy_(torch.from_numpy(lut3))
+    x = torch.from_numpy(rng.standard_normal((1, 1, K)).astype(np.float16)).cuda()
+    for bits, lut, idx in ((4, lut4, idx4), (3, lut3, idx4 >> 1)):
+        m.set_precision(bits)
+        y = m(x).float().cpu().numpy().reshape(1, N)
+        W = lut[np.arange(N)[:, None], idx]
+        y64 = oracle.gemv_f64(W, x.cpu().numpy())
+        assert _nerr(y, y64) <= TOL_TRUTH, bits
+        yp = m(x.expand(1, 3, K).contiguous())  # seq > 1 -> dequant + matmul
+        assert _nerr(yp[:, 0].float().cpu().numpy(), y64) <= 2e-3
+    with pytest.raises(RuntimeError):
+        m.set_precision(2)
+
+
+def test_aplinear_module_and_custom_op(oracle):
+    from guidedquant_b200.APLinear import APLinear
+
+    N, K, bits = 128, 4096, 2
+    idx, q, lut, x = oracle.synth_layer(N, K, bits, seed=77)
+    lin = APLinear(K, N, bits)
+    lin.qweight.copy_(torch.from_numpy(q))
+    lin.lut.copy_(torch.from_numpy(lut))
+    xq = torch.from_numpy(x).cuda()
+    y = lin(xq)
+    assert y.data_ptr() == lin.output.data_ptr()  # aliasing contract of the reference (APLinear.py:33,60)
+    y64 = oracle.gemv_f64(oracle.dequant(q, lut, bits), x)
+    assert _nerr(y.float().cpu().numpy(), y64) <= TOL_TRUTH
+    y2 = torch.zeros_like(lin.output)
+    torch.ops.plugin.anyprec_gemv(xq, lin.qweight, lin.lut, y2, bits)
+    assert torch.equal(y2, lin.output)
+    yp = lin(xq.expand(1, 4, K).contiguous())
+    assert yp.shape == (1, 4, N) and _nerr(yp[:, 1].float().cpu().numpy(), y64) <= 2e-3
+    # CUDA-graph capture of the op (how generate.py runs it)
+    g = torch.cuda.CUDAGraph()
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        lin(xq)
+        s.synchronize()
+        with torch.cuda.graph(g, stream=s):
+            lin(xq)
+        lin.output.zero_()
+        g.replay()
+        s.synchronize()
+    assert torch.equal(lin.output, y2)
