@@ -38,6 +38,9 @@ def parse():
     ap.add_argument("--layers", type=int, default=None, help="override layer count (debug only; invalidates the number)")
     ap.add_argument("--no-pdl", action="store_true")
     ap.add_argument("--ctas", type=int, default=0)
+    ap.add_argument("--workload", default="decode", choices=["decode", "gemv-chain"],
+                    help="decode: the whole token step (1 GPU); gemv-chain: only the 4*L APLinear GEMVs (always used for N > 1)")
+    ap.add_argument("--max-seq", type=int, default=512)
     ap.add_argument("--l2-prefetch", action="store_true", help="L2-prefetch the next Linear (measured slower on B200; off)")
     return ap.parse_args()
 
@@ -148,7 +151,10 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     model = a.model or "llama3-8b"  # same workload at every N so the scaling series is comparable (70B: --model llama3-70b)
-    workload = f"{model} {a.bits}-bit bs=1 decode, ap_gemv hot path ({'4*L' if a.layers is None else a.layers} APLinear GEMVs/token chain)"
+    full_decode = a.workload == "decode" and max(world, a.gpus) == 1 and a.impl == "ours"
+    workload = (f"{model} {a.bits}-bit bs=1 decode, full token step: embed + L x (wqkv|attn|wo|w1w3|w2) + lm_head + greedy sample"
+                if full_decode else
+                f"{model} {a.bits}-bit bs=1 decode, ap_gemv hot path only ({'4*L' if a.layers is None else a.layers} APLinear GEMVs/token chain)")
 
     if a.impl == "reference":
         if rank != 0:
@@ -169,6 +175,7 @@ def main():
     import torch
 
     from guidedquant_b200 import _lib
+    from guidedquant_b200.model import APTransformer
     from guidedquant_b200.runtime import ApGemvChain
 
     if not torch.cuda.is_available():
@@ -182,56 +189,78 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
         pg = dist.group.WORLD
 
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def timed(step_fn, stream, steps, warm):
+        for _ in range(warm):
+            step_fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            e0.record()
+        for _ in range(steps):
+            step_fn()
+        with torch.cuda.stream(stream):
+            e1.record()
+        barrier()
+        dt = e0.elapsed_time(e1) * 1e-3
+        if world > 1:
+            t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+            dt = float(t[0])
+        return dt
+
+    warm = max(3, a.warmup)
+    full = (a.workload == "decode") and world == 1
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+
+    # ---------------- the hot path alone: the per-token GEMV chain (always measured: it carries the roofline figure)
     chain = ApGemvChain(model, bits=a.bits, n_layer=a.layers, pdl=not a.no_pdl, world_size=world, rank=rank,
                         process_group=pg, ctas_per_sm=a.ctas, l2_prefetch=a.l2_prefetch)
     chain.capture()
     d = chain.cfg["dim"]
     x_host = torch.randn((1, 1, d)).half().pin_memory()
     chain.x_in.copy_(x_host)
+    args_steps_chain = a.steps
+    dt_chain = timed(chain.step, chain.stream, a.steps, warm)
+    if not full:
+        dt = dt_chain
+        dt_e2e = timed(lambda: chain.step_host(x_host), chain.stream, a.steps, 3)
+        launches, h2d, d2h = chain.launches_per_step, d * 2, d * 2
+    ab_chain = chain.algo_bytes_per_step()
+    n_gemv = 4 * chain.cfg["n_layer"]
+    wbytes = chain.weight_bytes()
 
-    def barrier():
-        if world > 1:
-            torch.distributed.barrier()
-        torch.cuda.synchronize()
+    # ---------------- the whole decode step (1 GPU): embed + L blocks (5 launches each) + lm_head + greedy sample
+    bytes_tok = None
+    if full:
+        chain.graph = None
+        del chain
+        torch.cuda.empty_cache()
+        tf = APTransformer(model, bits=a.bits, max_seq_len=a.max_seq, pdl=not a.no_pdl, n_layer=a.layers).random_init()
+        tf.capture()
+        n_tok = min(a.steps, a.max_seq - 2)
 
-    # ---------------- device-resident timing
-    for _ in range(max(3, a.warmup)):
-        chain.step()
-    barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with torch.cuda.stream(chain.stream):
-        e0.record()
-    for _ in range(a.steps):
-        chain.step()
-    with torch.cuda.stream(chain.stream):
-        e1.record()
-    barrier()
-    dt = e0.elapsed_time(e1) * 1e-3
-    # ---------------- end-to-end timing (host buffers, copies inside the timed region)
-    for _ in range(3):
-        chain.step_host(x_host)
-    barrier()
-    t0 = time.perf_counter()
-    with torch.cuda.stream(chain.stream):
-        e2 = torch.cuda.Event(enable_timing=True)
-        e2.record()
-    for _ in range(a.steps):
-        y = chain.step_host(x_host)
-    with torch.cuda.stream(chain.stream):
-        e3 = torch.cuda.Event(enable_timing=True)
-        e3.record()
-    barrier()
-    dt_e2e = max(e2.elapsed_time(e3) * 1e-3, 0.0)
-    dt_e2e_wall = time.perf_counter() - t0
+        def run_tokens(step_fn, n, w):
+            # every timed step is a NEW token at the next position (BOS-only prompt protocol, generate.py:310-313)
+            tf.reset(1)
+            return timed(step_fn, tf.stream, n, w)
+
+        tok_pinned = torch.ones(1, dtype=torch.int32).pin_memory()
+        warm_d = min(warm, max(1, a.max_seq - 2 - n_tok))
+        dt = run_tokens(tf.step, n_tok, warm_d)
+        dt_e2e = run_tokens(lambda: tf.step_host(tok_pinned), n_tok, min(3, warm_d))
+        a.steps = n_tok
+        launches, h2d, d2h = tf.launches_per_token, 4, 4
+        bytes_tok = tf.algo_bytes_per_token(pos=n_tok // 2)
+
     sampler.stop_flag = True
     sampler.join(timeout=1.0)
 
-    if world > 1:
-        t = torch.tensor([dt, dt_e2e], device="cuda", dtype=torch.float64)
-        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-        dt, dt_e2e = float(t[0]), float(t[1])
     def finish():
         # a live CUDA graph that captured NCCL kernels makes communicator teardown hang: drop the graph, sync,
         # and leave without tearing the communicator down
@@ -248,28 +277,34 @@ def main():
     tok_s = a.steps / dt
     ms = dt / a.steps * 1e3
     peak, peak_src = measured_peak_gbs()
-    ab = chain.algo_bytes_per_step()                 # per rank, all GEMV launches of one token
-    n_gemv = 4 * chain.cfg["n_layer"]
-    achieved = ab / (dt / a.steps) / 1e9             # GB/s per GPU over the whole step (includes launch gaps)
+    t_chain = dt_chain / args_steps_chain  # seconds per token of the GEMV chain alone
+    achieved = ab_chain / t_chain / 1e9          # GB/s per GPU of the GEMV launches (launch gaps included)
     line = {
-        "metric": METRIC, "value": tok_s, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(3, a.warmup),
+        "metric": METRIC, "value": tok_s, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": warm,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak", "vs_baseline": None,
         "dtype": "f16", "data": "synthetic",
         "config": {
             "workload": workload, "bits": a.bits, "gemv_launches_per_token": n_gemv,
             "parallelism": "single GPU" if world == 1 else f"tp{world}: wqkv/w1w3 N-sharded, wo/w2 K-sharded + NCCL all-reduce",
-            "l2_policy": "inputs larger than L2: every GEMV reads its own distinct weights (%.2f GB/token/GPU), streamed evict-first" % (chain.weight_bytes() / 1e9),
+            "l2_policy": "inputs larger than L2: every GEMV reads its own distinct weights (%.2f GB/token/GPU), streamed evict-first" % (wbytes / 1e9),
             "pdl": not a.no_pdl, "l2_prefetch_next_linear": a.l2_prefetch, "accumulate": "fp16 chains of 8 -> fp32",
         },
         "clocks": sampler.result(),
-        "e2e": {"value": a.steps / dt_e2e if dt_e2e > 0 else None, "unit": UNIT, "h2d_bytes_per_step": d * 2,
-                "d2h_bytes_per_step": d * 2, "wall_value": a.steps / dt_e2e_wall},
-        "gpu_launches": chain.launches_per_step * a.steps,
+        "e2e": {"value": a.steps / dt_e2e if dt_e2e > 0 else None, "unit": UNIT, "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h},
+        "gpu_launches": launches * a.steps,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": None, "peak_source": peak_src, "kernel": "apg::gemv_fast_kernel",
-                     "algorithmic_bytes_per_step": ab, "launches_per_step": n_gemv,
+                     "algorithmic_bytes_per_step": ab_chain, "launches_per_step": n_gemv,
+                     "timed_as": "the %d GEMV launches of a token replayed as their own CUDA graph in this process: %.1f us/token" % (n_gemv, t_chain * 1e6),
                      "frac_of_8TBs": achieved / 8000.0},
     }
+    if full:
+        line["config"]["max_seq_len"] = a.max_seq
+        line["config"]["launches_per_token"] = launches
+        line["config"]["sampling"] = "greedy (temperature 0), token and position advanced on the device"
+        line["decode_bytes"] = {"per_token": bytes_tok, "achieved_GBs_all_bytes": bytes_tok["total"] / (dt / a.steps) / 1e9,
+                                "frac_of_peak_all_bytes": bytes_tok["total"] / (dt / a.steps) / 1e9 / peak}
     # CPU baseline (rank 0, N = 1 only): bounded sample
     if world == 1:
         try:

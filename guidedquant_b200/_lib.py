@@ -91,9 +91,9 @@ def lib() -> ctypes.CDLL:
     L.apd_attn_decode.restype = i32
     L.apd_attn_decode.argtypes = [vp, vp, vp, vp, vp, vp, vp, u32, u32, u32, u32, f32, u32, vp]
     L.apd_lm_head.restype = i32
-    L.apd_lm_head.argtypes = [vp, vp, f32, vp, vp, u32, u32, u32, vp]
+    L.apd_lm_head.argtypes = [vp, vp, f32, vp, vp, u32, u32, vp, vp, ctypes.POINTER(u32), u32, vp]
     L.apd_argmax_advance.restype = i32
-    L.apd_argmax_advance.argtypes = [vp, u32, vp, vp, vp, u32, u32, vp]
+    L.apd_argmax_advance.argtypes = [vp, vp, u32, vp, vp, vp, u32, u32, vp]
     L.apg_prefetch_hint.restype = i32
     L.apg_prefetch_hint.argtypes = [vp, ctypes.c_uint64]
     L.apg_round_f32_to_f16.restype = i32

@@ -426,6 +426,7 @@ __global__ void __launch_bounds__(544, 1) gemv_fast_kernel(const FastParams p) {
     const uint32_t r_end = min(s_end * RS, N);
     const uint32_t nrows = r_end - r_begin;
 
+    __half res_pref = __ushort_as_half(0);  // residual of row r_begin + threadIdx.x, prefetched by consumer threads
     if (threadIdx.x == 0) {
         for (uint32_t s = 0; s < NS; s++) {
             mbar_init(bar_full + 8u * s, 1u);
@@ -483,8 +484,26 @@ __global__ void __launch_bounds__(544, 1) gemv_fast_kernel(const FastParams p) {
         typename Tb::Regs lr;
         if (g < nstages) Tb::fetch(lr, p.lut, r_begin + g * RS, N, lane);
 
+        // RMSNorm weights of this lane's k (static data: fetched before the dependency wait)
+        uint32_t wn[CPW][16];
+        if (p.norm_w) {
+#pragma unroll
+            for (int cc = 0; cc < CPW; cc++) {
+                const uint32_t i = wk * CPW + cc;
+                const uint32_t eff = (i < nchunk) ? chunk_eff(K, i) : 0u;
+                if ((uint32_t)lane < eff) {
+#pragma unroll
+                    for (int c = 0; c < 4; c++) {
+                        const uint4 wv = __ldg(reinterpret_cast<const uint4 *>(p.norm_w + i * 1024u + c * 8u * eff + 8u * lane));
+                        wn[cc][4 * c + 0] = wv.x, wn[cc][4 * c + 1] = wv.y, wn[cc][4 * c + 2] = wv.z, wn[cc][4 * c + 3] = wv.w;
+                    }
+                }
+            }
+        }
+
         // x -> registers (produced by the previous kernel on the stream: wait for it under PDL)
         pdl_wait_prior_grid();
+        if (p.residual && threadIdx.x < nrows) res_pref = p.residual[r_begin + threadIdx.x];
         uint32_t xr[CPW][16];
         bool act[CPW];
         uint32_t woff[CPW];  // byte offset of this lane's word inside a (row, plane)
@@ -536,19 +555,12 @@ __global__ void __launch_bounds__(544, 1) gemv_fast_kernel(const FastParams p) {
 #pragma unroll
             for (int cc = 0; cc < CPW; cc++) {
                 if (act[cc]) {
-                    const uint32_t i = wk * CPW + cc;
-                    const uint32_t eff = chunk_eff(K, i);
 #pragma unroll
-                    for (int c = 0; c < 4; c++) {
-                        const uint4 wv = __ldg(reinterpret_cast<const uint4 *>(p.norm_w + i * 1024u + c * 8u * eff + 8u * lane));
-                        const uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};
-#pragma unroll
-                        for (int e = 0; e < 4; e++) {
-                            const float2 f = __half22float2(*reinterpret_cast<const __half2 *>(&xr[cc][4 * c + e]));
-                            const __half2 n = __floats2half2_rn(f.x * rs, f.y * rs);  // .type_as(x)
-                            const __half2 r = __hmul2(n, *reinterpret_cast<const __half2 *>(&ww[e]));  // * weight
-                            xr[cc][4 * c + e] = *reinterpret_cast<const uint32_t *>(&r);
-                        }
+                    for (int e = 0; e < 16; e++) {
+                        const float2 f = __half22float2(*reinterpret_cast<const __half2 *>(&xr[cc][e]));
+                        const __half2 n = __floats2half2_rn(f.x * rs, f.y * rs);  // .type_as(x)
+                        const __half2 r = __hmul2(n, *reinterpret_cast<const __half2 *>(&wn[cc][e]));  // * weight
+                        xr[cc][e] = *reinterpret_cast<const uint32_t *>(&r);
                     }
                 }
             }
@@ -593,7 +605,7 @@ __global__ void __launch_bounds__(544, 1) gemv_fast_kernel(const FastParams p) {
         for (uint32_t w = 1; w < nwk; w++) v += red[r * nwk + w];
         if (p.out) {
             __half h = __float2half_rn(v);
-            if (p.residual) h = __hadd(h, p.residual[r_begin + r]);
+            if (p.residual) h = __hadd(h, (r == threadIdx.x && threadIdx.x < ncons * 32u) ? res_pref : p.residual[r_begin + r]);
             p.out[r_begin + r] = h;
         }
         if (p.partial) p.partial[r_begin + r] = v;

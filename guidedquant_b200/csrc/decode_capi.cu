@@ -43,7 +43,7 @@ int apd_attn_decode(const void *qkv, const float *inv_freq, void *k_cache, void 
     if (H == 0 || Hkv == 0 || H % Hkv || H / Hkv > 8 || S == 0 || nsplit == 0) return APG_ERR_SHAPE;
     if (nsplit > 1 && !part_ws) return APG_ERR_NULL;
     if (!al(qkv, 8) || !al(k_cache, 8) || !al(v_cache, 8) || !al(out, 8) || (part_ws && !al(part_ws, 16))) return APG_ERR_ALIGN;
-    int rc = launch(apd::attn_decode_kernel, dim3(Hkv, nsplit), dim3(32 * (H / Hkv)), 0, flags, stream,
+    int rc = launch(apd::attn_decode_kernel, dim3(H, nsplit), dim3(32 * apd::kAttnWarps), 0, flags, stream,
                     static_cast<const __half *>(qkv), inv_freq, static_cast<__half *>(k_cache),
                     static_cast<__half *>(v_cache), pos, static_cast<__half *>(out), part_ws, H, Hkv, S, scale);
     if (rc != APG_OK || nsplit == 1) return rc;
@@ -52,7 +52,7 @@ int apd_attn_decode(const void *qkv, const float *inv_freq, void *k_cache, void 
 }
 
 int apd_lm_head(const void *x, const void *norm_w, float eps, const void *W, void *logits, uint32_t V, uint32_t D,
-                uint32_t flags, void *stream) {
+                float *best_val, int *best_idx, uint32_t *n_partials, uint32_t flags, void *stream) {
     if (!x || !norm_w || !W || !logits) return APG_ERR_NULL;
     if (V == 0 || D == 0 || D % 256 || D > 8192) return APG_ERR_SHAPE;
     if (!al(W, 16) || !al(x, 2) || !al(norm_w, 2)) return APG_ERR_ALIGN;
@@ -62,11 +62,12 @@ int apd_lm_head(const void *x, const void *norm_w, float eps, const void *W, voi
     const uint32_t nv = D / 256;
     uint32_t grid = (uint32_t)sms * 2u;
     if (grid * 8u > V) grid = (V + 7) / 8;
+    if (n_partials) *n_partials = grid;
     const size_t smem = (size_t)D * sizeof(float);
     auto go = [&](auto kern) {
         return launch(kern, dim3(grid), dim3(256), smem, flags, stream, static_cast<const __half *>(x),
                       static_cast<const __half *>(norm_w), eps, static_cast<const __half *>(W),
-                      static_cast<__half *>(logits), V, D);
+                      static_cast<__half *>(logits), V, D, best_val, best_idx);
     };
     switch (nv) {
         case 1: return go(apd::lm_head_kernel<1>);
@@ -79,12 +80,12 @@ int apd_lm_head(const void *x, const void *norm_w, float eps, const void *W, voi
     }
 }
 
-int apd_argmax_advance(const void *logits, uint32_t V, int *token, int *pos, int *history, uint32_t history_len,
-                       uint32_t flags, void *stream) {
-    if (!logits || !token || !pos) return APG_ERR_NULL;
-    if (V == 0) return APG_ERR_SHAPE;
-    return launch(apd::argmax_advance_kernel, dim3(1), dim3(1024), 0, flags, stream, static_cast<const __half *>(logits),
-                  V, token, pos, history, history_len);
+int apd_argmax_advance(const float *best_val, const int *best_idx, uint32_t n, int *token, int *pos, int *history,
+                       uint32_t history_len, uint32_t flags, void *stream) {
+    if (!best_val || !best_idx || !token || !pos) return APG_ERR_NULL;
+    if (n == 0) return APG_ERR_SHAPE;
+    return launch(apd::argmax_advance_kernel, dim3(1), dim3(n >= 512 ? 1024 : 256), 0, flags, stream, best_val, best_idx, n,
+                  token, pos, history, history_len);
 }
 
 }  // extern "C"

@@ -20,10 +20,10 @@ namespace apd {
 __global__ void embed_kernel(const __half *__restrict__ emb, const int *__restrict__ token, __half *__restrict__ x,
                              uint32_t dim) {
     apg::pdl_wait_prior_grid();
+    apg::pdl_launch_dependents();  // the next kernel's weight prefetch may start now; it waits for us before reading x
     const uint4 *src = reinterpret_cast<const uint4 *>(emb + (size_t)(*token) * dim);
     uint4 *dst = reinterpret_cast<uint4 *>(x);
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < dim / 8; i += gridDim.x * blockDim.x) dst[i] = src[i];
-    apg::pdl_launch_dependents();
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -32,8 +32,7 @@ __global__ void embed_kernel(const __half *__restrict__ emb, const int *__restri
 //   inv_freq fp32 [64]                  1 / base^(2i/128)                                    (LlamaRotaryEmbedding)
 //   k_cache, v_cache fp16 [Hkv, S, 128]                                                      (KVCache, model.py:63-79)
 //   out      fp16 [H * 128]             attention output, input of wo
-// grid = (Hkv, nsplit); block = 32 * G threads, G = H / Hkv query heads per KV head; warp w serves query head
-// kvh*G + w and the time steps t = split, split + nsplit, ... <= pos.  head_dim is fixed at 128: a lane owns 4 dims.
+// head_dim is fixed at 128: in the 4-dims-per-lane layout a lane owns dims 4*lane..4*lane+3.
 // cos/sin are computed in fp32 and rounded to fp16, and q*cos + rotate_half(q)*sin is evaluated in fp16 exactly as the
 // reference's half tensors do (model.py:309-314, 396-405); scores, softmax and P.V accumulate in fp32.
 // nsplit > 1: each (head, split) writes an un-normalised partial (m, l, acc[128]) and attn_merge_kernel combines them.
@@ -41,35 +40,57 @@ __global__ void embed_kernel(const __half *__restrict__ emb, const int *__restri
 constexpr int kHeadDim = 128;
 constexpr int kPartStride = kHeadDim + 4;
 
-__device__ __forceinline__ void rope4(const __half (&v)[4], const __half (&partner)[4], int lane, float pos,
-                                      const float *__restrict__ inv_freq, __half (&o)[4]) {
+__device__ __forceinline__ void rope4(const __half (&v)[4], const __half (&partner)[4], int lane, const __half (&c)[4],
+                                      const __half (&s)[4], __half (&o)[4]) {
     // dims d = 4*lane + j; rotate_half: d < 64 -> -x[d+64], d >= 64 -> x[d-64]  (model.py:268-272)
     const bool hi = lane >= 16;
 #pragma unroll
     for (int j = 0; j < 4; j++) {
-        const int d = 4 * lane + j;
-        const float fr = pos * inv_freq[d & 63];
-        const __half c = __float2half_rn(cosf(fr)), s = __float2half_rn(sinf(fr));
         const __half rot = hi ? partner[j] : __hneg(partner[j]);
-        o[j] = __hadd(__hmul(v[j], c), __hmul(rot, s));
+        o[j] = __hadd(__hmul(v[j], c[j]), __hmul(rot, s[j]));
     }
 }
 
-__global__ void __launch_bounds__(256) attn_decode_kernel(const __half *__restrict__ qkv, const float *__restrict__ inv_freq,
-                                                          __half *__restrict__ k_cache, __half *__restrict__ v_cache,
-                                                          const int *__restrict__ pos_ptr, __half *__restrict__ out,
-                                                          float *__restrict__ part, uint32_t H, uint32_t Hkv, uint32_t S,
-                                                          float scale) {
-    apg::pdl_wait_prior_grid();
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const uint32_t G = H / Hkv, kvh = blockIdx.x, split = blockIdx.y, nsplit = gridDim.y;
-    const uint32_t h = kvh * G + w;
-    const int pos = *pos_ptr;
-    const float fpos = (float)pos;
+// grid = (H, nsplit), block = 32 * kAttnWarps.  The cached time steps are cut into blocks of 32 which are dealt
+// round-robin to the nsplit * kAttnWarps workers (warps), so the work is balanced at every position.  Per block a warp
+// runs three phases, all with many independent loads in flight (a first version walked the steps one by one and was
+// bound by one L2 round trip per step, 0.44 us/step):
+//   1. scores: lane <-> time step; each lane reads a whole K row (16 x 16 B, independent) against q held in smem
+//   2. running softmax state (m, l) per warp
+//   3. P.V: lane = (step mod 4, 16-dim group); 4 steps per instruction, 4x unrolled
+// The warps' (m, l, acc[128]) meet in shared memory; warp 0 merges them, adds the current step (whose k, v are still in
+// registers: the cache row written by this launch is never read by it) and writes the head's output or split partial.
+constexpr int kAttnWarps = 4;
 
-    // q, k_new, v_new of this head / kv head: 4 dims per lane
-    __half q[4], kn[4], vn[4], qp[4], kp[4];
-    {
+__global__ void __launch_bounds__(32 * kAttnWarps) attn_decode_kernel(
+    const __half *__restrict__ qkv, const float *__restrict__ inv_freq, __half *__restrict__ k_cache,
+    __half *__restrict__ v_cache, const int *__restrict__ pos_ptr, __half *__restrict__ out, float *__restrict__ part,
+    uint32_t H, uint32_t Hkv, uint32_t S, float scale) {
+    __shared__ __align__(16) float qs[kHeadDim];                    // roped q (fp32)
+    __shared__ __align__(16) float sc[kAttnWarps][32];              // scores / probabilities of the block in flight
+    __shared__ __align__(16) float wacc[kAttnWarps][kHeadDim + 4];  // per-warp (m, l, -, -, acc[128])
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const uint32_t G = H / Hkv, h = blockIdx.x, kvh = h / G, split = blockIdx.y, nsplit = gridDim.y;
+    float fr4[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) fr4[j] = inv_freq[(4 * lane + j) & 63];  // static table: before the dependency wait
+    apg::pdl_wait_prior_grid();
+    apg::pdl_launch_dependents();  // wo's weight stream may start while we attend; it waits for us before reading `out`
+    const int pos = *pos_ptr;
+
+    // warp 0: RoPE of q and of the new k, KV append, q -> smem
+    __half kr[4], vn[4];
+    float qf[4];
+    if (w == 0) {
+        const float fpos = (float)pos;
+        __half rc[4], rs[4];  // cos / sin in fp32, rounded to fp16 (model.py:396-405), shared by q and k
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            float sn, cs;
+            sincosf(fpos * fr4[j], &sn, &cs);
+            rc[j] = __float2half_rn(cs), rs[j] = __float2half_rn(sn);
+        }
+        __half q[4], kn[4], qp[4], kp[4], qr[4];
         const uint2 qv = *reinterpret_cast<const uint2 *>(qkv + (size_t)h * kHeadDim + 4 * lane);
         const uint2 kv = *reinterpret_cast<const uint2 *>(qkv + (size_t)(H + kvh) * kHeadDim + 4 * lane);
         const uint2 vv = *reinterpret_cast<const uint2 *>(qkv + (size_t)(H + Hkv + kvh) * kHeadDim + 4 * lane);
@@ -78,58 +99,159 @@ __global__ void __launch_bounds__(256) attn_decode_kernel(const __half *__restri
         qpv.x = __shfl_xor_sync(0xffffffffu, qv.x, 16), qpv.y = __shfl_xor_sync(0xffffffffu, qv.y, 16);
         kpv.x = __shfl_xor_sync(0xffffffffu, kv.x, 16), kpv.y = __shfl_xor_sync(0xffffffffu, kv.y, 16);
         *reinterpret_cast<uint2 *>(qp) = qpv, *reinterpret_cast<uint2 *>(kp) = kpv;
-    }
-    __half qr[4], kr[4];
-    rope4(q, qp, lane, fpos, inv_freq, qr);
-    rope4(kn, kp, lane, fpos, inv_freq, kr);
-    if (split == 0 && w == 0) {  // cache append (KVCache.update, model.py:70-79); readers of t = pos use registers
-        *reinterpret_cast<uint2 *>(k_cache + ((size_t)kvh * S + pos) * kHeadDim + 4 * lane) = *reinterpret_cast<uint2 *>(kr);
-        *reinterpret_cast<uint2 *>(v_cache + ((size_t)kvh * S + pos) * kHeadDim + 4 * lane) = *reinterpret_cast<uint2 *>(vn);
-    }
-    float qf[4];
-#pragma unroll
-    for (int j = 0; j < 4; j++) qf[j] = __half2float(qr[j]);
-
-    float m = -CUDART_INF_F, l = 0.f, acc[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int t = (int)split; t <= pos; t += (int)nsplit) {
-        __half kk[4], vv[4];
-        if (t == pos) {
-#pragma unroll
-            for (int j = 0; j < 4; j++) kk[j] = kr[j], vv[j] = vn[j];
-        } else {
-            *reinterpret_cast<uint2 *>(kk) = *reinterpret_cast<const uint2 *>(k_cache + ((size_t)kvh * S + t) * kHeadDim + 4 * lane);
-            *reinterpret_cast<uint2 *>(vv) = *reinterpret_cast<const uint2 *>(v_cache + ((size_t)kvh * S + t) * kHeadDim + 4 * lane);
+        rope4(q, qp, lane, rc, rs, qr);
+        rope4(kn, kp, lane, rc, rs, kr);
+        if (split == 0 && h == kvh * G) {  // cache append (KVCache.update, model.py:70-79), once per KV head
+            *reinterpret_cast<uint2 *>(k_cache + ((size_t)kvh * S + pos) * kHeadDim + 4 * lane) = *reinterpret_cast<uint2 *>(kr);
+            *reinterpret_cast<uint2 *>(v_cache + ((size_t)kvh * S + pos) * kHeadDim + 4 * lane) = *reinterpret_cast<uint2 *>(vn);
         }
-        float s = 0.f;
 #pragma unroll
-        for (int j = 0; j < 4; j++) s = fmaf(qf[j], __half2float(kk[j]), s);
+        for (int j = 0; j < 4; j++) qf[j] = __half2float(qr[j]);
+        *reinterpret_cast<float4 *>(qs + 4 * lane) = make_float4(qf[0], qf[1], qf[2], qf[3]);
+    }
+    __syncthreads();
+
+    const __half *Kb = k_cache + (size_t)kvh * S * kHeadDim;
+    const __half *Vb = v_cache + (size_t)kvh * S * kHeadDim;
+    const int nblk = (pos + 31) >> 5;  // blocks of cached steps t < pos
+    const int tg = lane >> 3, dg = lane & 7;
+    float m = -CUDART_INF_F, l = 0.f, acc[16];
 #pragma unroll
-        for (int o = 16; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        s *= scale;
-        const float mn = fmaxf(m, s);
-        const float corr = __expf(m - mn), pe = __expf(s - mn);
-        l = l * corr + pe;
+    for (int j = 0; j < 16; j++) acc[j] = 0.f;
+
+    for (int b = (int)(split * kAttnWarps) + w; b < nblk; b += (int)(nsplit * kAttnWarps)) {
+        const int tb = b << 5, nt = min(32, pos - tb);
+        // ---- phase 1: scores of the block
+        float s = -CUDART_INF_F;
+        if (lane < nt) {
+            const uint4 *kr4 = reinterpret_cast<const uint4 *>(Kb + (size_t)(tb + lane) * kHeadDim);
+            uint4 kv[16];
 #pragma unroll
-        for (int j = 0; j < 4; j++) acc[j] = acc[j] * corr + pe * __half2float(vv[j]);
+            for (int i = 0; i < 16; i++) kv[i] = kr4[i];
+            float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                const float4 qa = *reinterpret_cast<const float4 *>(qs + 8 * i);
+                const float4 qb = *reinterpret_cast<const float4 *>(qs + 8 * i + 4);
+                const float2 k0 = __half22float2(*reinterpret_cast<const __half2 *>(&kv[i].x));
+                const float2 k1 = __half22float2(*reinterpret_cast<const __half2 *>(&kv[i].y));
+                const float2 k2 = __half22float2(*reinterpret_cast<const __half2 *>(&kv[i].z));
+                const float2 k3 = __half22float2(*reinterpret_cast<const __half2 *>(&kv[i].w));
+                a0 = fmaf(qa.x, k0.x, a0), a1 = fmaf(qa.y, k0.y, a1);
+                a0 = fmaf(qa.z, k1.x, a0), a1 = fmaf(qa.w, k1.y, a1);
+                a0 = fmaf(qb.x, k2.x, a0), a1 = fmaf(qb.y, k2.y, a1);
+                a0 = fmaf(qb.z, k3.x, a0), a1 = fmaf(qb.w, k3.y, a1);
+            }
+            s = (a0 + a1) * scale;
+        }
+        // ---- phase 2: online softmax update
+        float bm = s;
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, o));
+        const float mn = fmaxf(m, bm);
+        const float corr = __expf(m - mn);
+        const float pe = (lane < nt) ? __expf(s - mn) : 0.f;
+        float bl = pe;
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) bl += __shfl_xor_sync(0xffffffffu, bl, o);
+        l = l * corr + bl;
         m = mn;
+        __syncwarp();
+        sc[w][lane] = pe;
+        __syncwarp();
+        // ---- phase 3: acc = acc * corr + P.V of the block
+#pragma unroll
+        for (int j = 0; j < 16; j++) acc[j] *= corr;
+#pragma unroll
+        for (int hb = 0; hb < 2; hb++) {
+            uint4 va[4], vb[4];
+            float pw[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int tt = 16 * hb + 4 * u + tg;
+                pw[u] = 0.f;
+                va[u] = vb[u] = make_uint4(0, 0, 0, 0);
+                if (tt < nt) {
+                    const uint4 *vr = reinterpret_cast<const uint4 *>(Vb + (size_t)(tb + tt) * kHeadDim + 16 * dg);
+                    va[u] = vr[0], vb[u] = vr[1];
+                    pw[u] = sc[w][tt];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const uint32_t wv[8] = {va[u].x, va[u].y, va[u].z, va[u].w, vb[u].x, vb[u].y, vb[u].z, vb[u].w};
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const float2 f = __half22float2(*reinterpret_cast<const __half2 *>(&wv[j]));
+                    acc[2 * j] = fmaf(pw[u], f.x, acc[2 * j]);
+                    acc[2 * j + 1] = fmaf(pw[u], f.y, acc[2 * j + 1]);
+                }
+            }
+        }
+    }
+    // sum the four step groups of the warp; lanes with tg == 0 publish the warp's state
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+        acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 8);
+        acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 16);
+    }
+    if (lane == 0) wacc[w][0] = m, wacc[w][1] = l;
+    if (tg == 0) {
+#pragma unroll
+        for (int j = 0; j < 16; j += 4)
+            *reinterpret_cast<float4 *>(&wacc[w][4 + 16 * dg + j]) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+    }
+    __syncthreads();
+    if (w != 0) return;
+
+    // ---- warp 0: merge the warps' states (+ the current step on split 0); lane owns dims 4*lane..4*lane+3
+    float s_cur = -CUDART_INF_F;
+    if (split == 0) {
+        float d = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; j++) d = fmaf(qf[j], __half2float(kr[j]), d);
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+        s_cur = d * scale;
+    }
+    float M = s_cur;
+#pragma unroll
+    for (int i = 0; i < kAttnWarps; i++) M = fmaxf(M, wacc[i][0]);
+    float Lsum = 0.f, a4[4] = {0.f, 0.f, 0.f, 0.f};
+    if (M > -CUDART_INF_F) {
+#pragma unroll
+        for (int i = 0; i < kAttnWarps; i++) {
+            if (wacc[i][1] > 0.f) {
+                const float c = __expf(wacc[i][0] - M);
+                Lsum += wacc[i][1] * c;
+                const float4 v = *reinterpret_cast<const float4 *>(&wacc[i][4 + 4 * lane]);
+                a4[0] = fmaf(v.x, c, a4[0]), a4[1] = fmaf(v.y, c, a4[1]), a4[2] = fmaf(v.z, c, a4[2]), a4[3] = fmaf(v.w, c, a4[3]);
+            }
+        }
+        if (split == 0) {
+            const float pc = __expf(s_cur - M);
+            Lsum += pc;
+#pragma unroll
+            for (int j = 0; j < 4; j++) a4[j] = fmaf(pc, __half2float(vn[j]), a4[j]);
+        }
     }
     if (nsplit == 1) {
-        const float inv = 1.f / l;
-        __half o4[4];
+        const float inv = 1.f / Lsum;
+        __half r4[4];
 #pragma unroll
-        for (int j = 0; j < 4; j++) o4[j] = __float2half_rn(acc[j] * inv);
-        *reinterpret_cast<uint2 *>(out + (size_t)h * kHeadDim + 4 * lane) = *reinterpret_cast<uint2 *>(o4);
+        for (int j = 0; j < 4; j++) r4[j] = __float2half_rn(a4[j] * inv);
+        *reinterpret_cast<uint2 *>(out + (size_t)h * kHeadDim + 4 * lane) = *reinterpret_cast<uint2 *>(r4);
     } else {
         float *pp = part + ((size_t)h * nsplit + split) * kPartStride;  // (m, l, -, -, acc[128]): 16-byte aligned rows
-        if (lane == 0) pp[0] = m, pp[1] = l;
-        *reinterpret_cast<float4 *>(pp + 4 + 4 * lane) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        if (lane == 0) pp[0] = M, pp[1] = Lsum;
+        *reinterpret_cast<float4 *>(pp + 4 + 4 * lane) = make_float4(a4[0], a4[1], a4[2], a4[3]);
     }
-    apg::pdl_launch_dependents();
 }
 
 // combine nsplit partial softmax states per head: grid = H, block = 128
 __global__ void attn_merge_kernel(const float *__restrict__ part, __half *__restrict__ out, uint32_t nsplit) {
     apg::pdl_wait_prior_grid();
+    apg::pdl_launch_dependents();
     const uint32_t h = blockIdx.x, d = threadIdx.x;
     const float *pp = part + (size_t)h * nsplit * kPartStride;
     float m = -CUDART_INF_F;
@@ -144,7 +266,6 @@ __global__ void attn_merge_kernel(const float *__restrict__ part, __half *__rest
         }
     }
     out[(size_t)h * kHeadDim + d] = __float2half_rn(a / l);
-    apg::pdl_launch_dependents();
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -152,12 +273,26 @@ __global__ void attn_merge_kernel(const float *__restrict__ part, __half *__rest
 // x load, fp32 accumulation, fp16 logits (the reference's nn.Linear is fp16).  One warp per row, D % 256 == 0.
 // HBM-bound: 2*V*D bytes (1.05 GB for Llama-3: 37% of all bytes of a 2-bit token).
 // ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 ldg_evict_first_v4(const uint4 *p, uint64_t pol) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p), "l"(pol));
+    return r;
+}
+
+// total order on (value, index): larger value first, then smaller index; NaN never wins
+__device__ __forceinline__ bool better(float v, int i, float bv, int bi) { return v > bv || (v == bv && i < bi); }
+
 template <int NV>  // NV = D / 256: uint4 loads per lane per row
 __global__ void __launch_bounds__(256) lm_head_kernel(const __half *__restrict__ x, const __half *__restrict__ norm_w, float eps,
                                                       const __half *__restrict__ W, __half *__restrict__ logits, uint32_t V,
-                                                      uint32_t D) {
+                                                      uint32_t D, float *__restrict__ best_val, int *__restrict__ best_idx) {
     extern __shared__ __align__(16) float xs[];  // [D] normalised activations as fp32
     __shared__ float red[8];
+    __shared__ int redi[8];
+    uint64_t pol;  // the 2*V*D-byte weight is read once per token: keep it from evicting LUTs / KV / activations in L2
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
     apg::pdl_wait_prior_grid();
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
     float ss = 0.f;
@@ -181,11 +316,13 @@ __global__ void __launch_bounds__(256) lm_head_kernel(const __half *__restrict__
     apg::pdl_launch_dependents();
 
     const uint32_t warps_total = gridDim.x * nw;
+    float bv = -CUDART_INF_F;
+    int bi = 0;
     for (uint32_t row = blockIdx.x * nw + w; row < V; row += warps_total) {
         const uint4 *wr = reinterpret_cast<const uint4 *>(W + (size_t)row * D);
         uint4 v[NV];
 #pragma unroll
-        for (int i = 0; i < NV; i++) v[i] = apg::ldg_stream_v4(wr + i * 32 + lane);
+        for (int i = 0; i < NV; i++) v[i] = ldg_evict_first_v4(wr + i * 32 + lane, pol);
         float a0 = 0.f, a1 = 0.f;
 #pragma unroll
         for (int i = 0; i < NV; i++) {
@@ -203,7 +340,21 @@ __global__ void __launch_bounds__(256) lm_head_kernel(const __half *__restrict__
         float a = a0 + a1;
 #pragma unroll
         for (int o = 16; o >= 1; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-        if (lane == 0) logits[row] = __float2half_rn(a);
+        const __half lg = __float2half_rn(a);
+        if (lane == 0) logits[row] = lg;
+        const float lf = __half2float(lg);  // sampling sees the fp16 logits, like the reference (generate.py:69)
+        if (better(lf, (int)row, bv, bi)) bv = lf, bi = (int)row;
+    }
+    // per-CTA arg-max partial for the greedy sampler (rows ascend per warp, so ties keep the smaller index)
+    if (best_val) {
+        __syncthreads();
+        if (lane == 0) red[w] = bv, redi[w] = bi;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int i = 1; i < nw; i++)
+                if (better(red[i], redi[i], bv, bi)) bv = red[i], bi = redi[i];
+            best_val[blockIdx.x] = bv, best_idx[blockIdx.x] = bi;
+        }
     }
 }
 
@@ -212,34 +363,34 @@ __global__ void __launch_bounds__(256) lm_head_kernel(const __half *__restrict__
 // index wins ties like torch.argmax).  One CTA.  Writes the next token, appends it to the output ring and advances
 // the device-side position so the same graph can be replayed for the next token.
 // ------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) argmax_advance_kernel(const __half *__restrict__ logits, uint32_t V, int *token,
-                                                              int *pos, int *history, uint32_t history_len) {
+__global__ void __launch_bounds__(1024) argmax_advance_kernel(const float *__restrict__ best_val, const int *__restrict__ best_idx,
+                                                              uint32_t n, int *token, int *pos, int *history,
+                                                              uint32_t history_len) {
     apg::pdl_wait_prior_grid();
+    apg::pdl_launch_dependents();
     __shared__ float bv[32];
     __shared__ int bi[32];
     float best = -CUDART_INF_F;
-    int idx = 0x7fffffff;
-    for (uint32_t i = threadIdx.x; i < V; i += blockDim.x) {
-        const float f = __half2float(logits[i]);
-        if (f > best || (f == best && (int)i < idx)) best = f, idx = (int)i;
-    }
+    int idx = 0;
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x)
+        if (better(best_val[i], best_idx[i], best, idx)) best = best_val[i], idx = best_idx[i];
 #pragma unroll
     for (int o = 16; o >= 1; o >>= 1) {
         const float ob = __shfl_xor_sync(0xffffffffu, best, o);
         const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
-        if (ob > best || (ob == best && oi < idx)) best = ob, idx = oi;
+        if (better(ob, oi, best, idx)) best = ob, idx = oi;
     }
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     if (lane == 0) bv[w] = best, bi[w] = idx;
     __syncthreads();
     if (w == 0) {
         best = lane < (int)(blockDim.x >> 5) ? bv[lane] : -CUDART_INF_F;
-        idx = lane < (int)(blockDim.x >> 5) ? bi[lane] : 0x7fffffff;
+        idx = lane < (int)(blockDim.x >> 5) ? bi[lane] : 0;
 #pragma unroll
         for (int o = 16; o >= 1; o >>= 1) {
             const float ob = __shfl_xor_sync(0xffffffffu, best, o);
             const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
-            if (ob > best || (ob == best && oi < idx)) best = ob, idx = oi;
+            if (better(ob, oi, best, idx)) best = ob, idx = oi;
         }
         if (lane == 0) {
             const int p = *pos;
@@ -248,7 +399,6 @@ __global__ void __launch_bounds__(1024) argmax_advance_kernel(const __half *__re
             *pos = p + 1;
         }
     }
-    apg::pdl_launch_dependents();
 }
 
 }  // namespace apd

@@ -53,6 +53,8 @@ class APTransformer:
         self.att = torch.zeros(d, dtype=f16, device=dev)
         self.gu = torch.zeros(self.shapes["w1w3"][0], dtype=f16, device=dev)
         self.logits = torch.zeros(c["vocab"], dtype=f16, device=dev)
+        self.best_val = torch.zeros(4096, dtype=torch.float32, device=dev)   # per-CTA arg-max partials of lm_head
+        self.best_idx = torch.zeros(4096, dtype=torch.int32, device=dev)
         self.token = torch.zeros(1, dtype=torch.int32, device=dev)
         self.pos = torch.zeros(1, dtype=torch.int32, device=dev)
         self.history = torch.zeros(max_seq_len + 1, dtype=torch.int32, device=dev)
@@ -65,6 +67,7 @@ class APTransformer:
         self.stream = torch.cuda.Stream(device=dev)
         self.tok_host = torch.zeros(1, dtype=torch.int32).pin_memory()
         self.launches_per_token = 0
+        self.debug_skip: set[str] = set()  # profiling aid only: {"attn", "lm_head", "sample", "embed", "fusion"}
 
     # ------------------------------------------------------------------ weights
     def random_init(self, seed: int = 0):
@@ -103,6 +106,8 @@ class APTransformer:
     def _fused(self, x, out, name, N, K, norm=None, silu_mul=0, residual=None):
         L = _lib.lib()
         q, lut = self.sd[name + ".qweight"], self.sd[name + ".lut"]
+        if "fusion" in self.debug_skip:
+            norm, silu_mul, residual = None, 0, None
         st = L.apg_gemv_fused(x.data_ptr(), out.data_ptr(), None, q.data_ptr(), lut.data_ptr(), N, K, self.bits,
                               norm.data_ptr() if norm is not None else None, self.eps, silu_mul,
                               residual.data_ptr() if residual is not None else None, self.flags,
@@ -115,24 +120,33 @@ class APTransformer:
         L, c, sd, fl = _lib.lib(), self.cfg, self.sd, self.flags
         st = torch.cuda.current_stream().cuda_stream
         self.launches_per_token = 0
-        _lib.check(L.apd_embed(sd["tok_embeddings.weight"].data_ptr(), self.token.data_ptr(), self.x.data_ptr(), c["dim"], fl, st), "apd_embed")
-        self.launches_per_token += 1
+        if "embed" not in self.debug_skip:
+            _lib.check(L.apd_embed(sd["tok_embeddings.weight"].data_ptr(), self.token.data_ptr(), self.x.data_ptr(), c["dim"], fl, st), "apd_embed")
+            self.launches_per_token += 1
         scale = 1.0 / math.sqrt(128.0)
         for i in range(c["n_layer"]):
             p = f"layers.{i}."
             (nq, kq), (no, ko), (ng, kg), (n2, k2) = (self.shapes[n] for n in ("wqkv", "wo", "w1w3", "w2"))
             self._fused(self.x, self.qkv, p + "attention.wqkv", nq, kq, norm=sd[p + "input_layernorm.weight"])
-            _lib.check(L.apd_attn_decode(self.qkv.data_ptr(), self.inv_freq.data_ptr(), self.k_cache[i].data_ptr(),
+            if "attn" not in self.debug_skip:
+              _lib.check(L.apd_attn_decode(self.qkv.data_ptr(), self.inv_freq.data_ptr(), self.k_cache[i].data_ptr(),
                                          self.v_cache[i].data_ptr(), self.pos.data_ptr(), self.att.data_ptr(),
                                          self.part.data_ptr() if self.part is not None else None, c["n_head"], c["n_kv"],
                                          self.S, self.nsplit, scale, fl, st), "apd_attn_decode")
-            self.launches_per_token += 1 + (1 if self.nsplit > 1 else 0)
+              self.launches_per_token += 1 + (1 if self.nsplit > 1 else 0)
             self._fused(self.att, self.h, p + "attention.wo", no, ko, residual=self.x)
             self._fused(self.h, self.gu, p + "feed_forward.w1w3", ng, kg, norm=sd[p + "post_attention_layernorm.weight"])
             self._fused(self.gu, self.x, p + "feed_forward.w2", n2, k2, silu_mul=1, residual=self.h)
-        _lib.check(L.apd_lm_head(self.x.data_ptr(), sd["norm.weight"].data_ptr(), self.eps, sd["output.weight"].data_ptr(),
-                                 self.logits.data_ptr(), c["vocab"], c["dim"], fl, st), "apd_lm_head")
-        _lib.check(L.apd_argmax_advance(self.logits.data_ptr(), c["vocab"], self.token.data_ptr(), self.pos.data_ptr(),
+        if "lm_head" not in self.debug_skip:
+          import ctypes
+          npart = ctypes.c_uint32(0)
+          _lib.check(L.apd_lm_head(self.x.data_ptr(), sd["norm.weight"].data_ptr(), self.eps, sd["output.weight"].data_ptr(),
+                                 self.logits.data_ptr(), c["vocab"], c["dim"], self.best_val.data_ptr(),
+                                 self.best_idx.data_ptr(), ctypes.byref(npart), fl, st), "apd_lm_head")
+          self._npart = npart.value
+        if "sample" not in self.debug_skip:
+          _lib.check(L.apd_argmax_advance(self.best_val.data_ptr(), self.best_idx.data_ptr(), self._npart,
+                                        self.token.data_ptr(), self.pos.data_ptr(),
                                         self.history.data_ptr(), self.history.numel(), fl, st), "apd_argmax_advance")
         self.launches_per_token += 2
 

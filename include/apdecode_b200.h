@@ -23,14 +23,16 @@ int apd_attn_decode(const void *qkv, const float *inv_freq, void *k_cache, void 
                     float *part_ws, uint32_t H, uint32_t Hkv, uint32_t S, uint32_t nsplit, float scale, uint32_t flags,
                     void *stream);
 
-/* logits[V] (fp16) = W[V,D] . (RMSNorm(x) * norm_w)      Transformer.forward tail, model.py:128-129.  D % 256 == 0, D <= 8192. */
+/* logits[V] (fp16) = W[V,D] . (RMSNorm(x) * norm_w)      Transformer.forward tail, model.py:128-129.  D % 256 == 0, D <= 8192.
+ * best_val/best_idx (optional, >= 2*SMs entries each): per-CTA arg-max partials of the fp16 logits for apd_argmax_advance;
+ * *n_partials (optional, host) receives how many entries were written (= the grid size). */
 int apd_lm_head(const void *x, const void *norm_w, float eps, const void *W, void *logits, uint32_t V, uint32_t D,
-                uint32_t flags, void *stream);
+                float *best_val, int *best_idx, uint32_t *n_partials, uint32_t flags, void *stream);
 
-/* greedy sampling (generate.py:55-73 at temperature 0): *token = argmax(logits) (first index on ties);
- * history[*pos + 1] = *token (if history != NULL and in range); *pos += 1. */
-int apd_argmax_advance(const void *logits, uint32_t V, int *token, int *pos, int *history, uint32_t history_len,
-                       uint32_t flags, void *stream);
+/* greedy sampling (generate.py:55-73 at temperature 0) from apd_lm_head's partials: *token = argmax(logits) (first index
+ * on ties; NaN never wins); history[*pos + 1] = *token (if history != NULL and in range); *pos += 1. */
+int apd_argmax_advance(const float *best_val, const int *best_idx, uint32_t n, int *token, int *pos, int *history,
+                       uint32_t history_len, uint32_t flags, void *stream);
 
 #ifdef __cplusplus
 }
