@@ -526,7 +526,10 @@ __global__ void __launch_bounds__(544, 1) gemv_fast_kernel(const FastParams p) {
 #pragma unroll
                         for (int e = 0; e < 4; e++) {
                             const float2 gf = __half22float2(*reinterpret_cast<const __half2 *>(&xr[cc][4 * c + e]));
-                            const __half2 sg = __floats2half2_rn(gf.x / (1.f + __expf(-gf.x)), gf.y / (1.f + __expf(-gf.y)));
+                            // silu in fp32 with the fast reciprocal (2 ulp, invisible after the fp16 rounding); an IEEE
+                            // division here costs ~400 serial instructions per warp on the critical path of every w2
+                            const __half2 sg = __floats2half2_rn(__fdividef(gf.x, 1.f + __expf(-gf.x)),
+                                                                 __fdividef(gf.y, 1.f + __expf(-gf.y)));
                             const __half2 r = __hmul2(sg, *reinterpret_cast<const __half2 *>(&uu[e]));
                             xr[cc][4 * c + e] = *reinterpret_cast<const uint32_t *>(&r);
                         }

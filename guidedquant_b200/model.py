@@ -67,6 +67,9 @@ class APTransformer:
         self.stream = torch.cuda.Stream(device=dev)
         self.tok_host = torch.zeros(1, dtype=torch.int32).pin_memory()
         self.launches_per_token = 0
+        # measured on B200: launching the 1 GB lm_head stream programmatically (early, beside the last w2) costs
+        # ~250 us/token; it is launched as a plain stream-ordered kernel instead
+        self.lm_head_no_pdl = _lib.APG_FLAG_PDL
         self.debug_skip: set[str] = set()  # profiling aid only: {"attn", "lm_head", "sample", "embed", "fusion"}
 
     # ------------------------------------------------------------------ weights
@@ -108,6 +111,12 @@ class APTransformer:
         q, lut = self.sd[name + ".qweight"], self.sd[name + ".lut"]
         if "fusion" in self.debug_skip:
             norm, silu_mul, residual = None, 0, None
+        if "norm" in self.debug_skip:
+            norm = None
+        if "silu" in self.debug_skip:
+            silu_mul = 0
+        if "residual" in self.debug_skip:
+            residual = None
         st = L.apg_gemv_fused(x.data_ptr(), out.data_ptr(), None, q.data_ptr(), lut.data_ptr(), N, K, self.bits,
                               norm.data_ptr() if norm is not None else None, self.eps, silu_mul,
                               residual.data_ptr() if residual is not None else None, self.flags,
@@ -142,7 +151,7 @@ class APTransformer:
           npart = ctypes.c_uint32(0)
           _lib.check(L.apd_lm_head(self.x.data_ptr(), sd["norm.weight"].data_ptr(), self.eps, sd["output.weight"].data_ptr(),
                                  self.logits.data_ptr(), c["vocab"], c["dim"], self.best_val.data_ptr(),
-                                 self.best_idx.data_ptr(), ctypes.byref(npart), fl, st), "apd_lm_head")
+                                 self.best_idx.data_ptr(), ctypes.byref(npart), fl & ~self.lm_head_no_pdl, st), "apd_lm_head")
           self._npart = npart.value
         if "sample" not in self.debug_skip:
           _lib.check(L.apd_argmax_advance(self.best_val.data_ptr(), self.best_idx.data_ptr(), self._npart,

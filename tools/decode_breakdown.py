@@ -7,7 +7,7 @@ sys.path.insert(0, ROOT)
 from guidedquant_b200.model import APTransformer
 model = sys.argv[1] if len(sys.argv) > 1 else "llama3-8b"
 bits = int(sys.argv[2]) if len(sys.argv) > 2 else 2
-tf = APTransformer(model, bits=bits, max_seq_len=512).random_init()
+tf = APTransformer(model, bits=bits, max_seq_len=512, pdl=os.environ.get("NOPDL") is None).random_init()
 def run(skip, n=100):
     tf.debug_skip = set(skip); tf.graph = None; tf.capture(); tf.reset(1)
     for _ in range(10): tf.step()
@@ -19,5 +19,11 @@ def run(skip, n=100):
         e1.record()
     tf.stream.synchronize()
     return e0.elapsed_time(e1) / n * 1e3
-for skip in ([], ["sample"], ["sample", "lm_head"], ["sample", "lm_head", "attn"], ["sample", "lm_head", "attn", "fusion"], ["sample", "lm_head", "attn", "fusion", "embed"], ["attn"], ["fusion"]):
+import itertools
+cfgs = [[], ["sample", "attn", "fusion"], ["sample", "attn", "lm_head", "fusion"], ["sample", "attn", "lm_head", "norm"],
+        ["sample", "attn", "lm_head", "residual"], ["sample", "attn", "lm_head", "silu"], ["sample", "attn", "lm_head", "norm", "residual"],
+        ["sample", "attn", "lm_head"]]
+if len(sys.argv) > 3:
+    cfgs = [c.split(",") if c else [] for c in sys.argv[3].split(";")]
+for skip in cfgs:
     print(json.dumps({"skip": skip, "us_per_token": round(run(skip), 1)}), flush=True)
