@@ -41,6 +41,8 @@ def parse():
     ap.add_argument("--workload", default="decode", choices=["decode", "gemv-chain"],
                     help="decode: the whole token step (1 GPU); gemv-chain: only the 4*L APLinear GEMVs (always used for N > 1)")
     ap.add_argument("--max-seq", type=int, default=512)
+    ap.add_argument("--collective", default="push", choices=["push", "nccl"],
+                    help="N > 1: fused one-shot all-reduce pushed from the GEMV epilogue over NVLink peer memory, or NCCL")
     ap.add_argument("--l2-prefetch", action="store_true", help="L2-prefetch the next Linear (measured slower on B200; off)")
     return ap.parse_args()
 
@@ -220,7 +222,7 @@ def main():
 
     # ---------------- the hot path alone: the per-token GEMV chain (always measured: it carries the roofline figure)
     chain = ApGemvChain(model, bits=a.bits, n_layer=a.layers, pdl=not a.no_pdl, world_size=world, rank=rank,
-                        process_group=pg, ctas_per_sm=a.ctas, l2_prefetch=a.l2_prefetch)
+                        process_group=pg, ctas_per_sm=a.ctas, l2_prefetch=a.l2_prefetch, collective=a.collective)
     chain.capture()
     d = chain.cfg["dim"]
     x_host = torch.randn((1, 1, d)).half().pin_memory()
@@ -285,7 +287,7 @@ def main():
         "dtype": "f16", "data": "synthetic",
         "config": {
             "workload": workload, "bits": a.bits, "gemv_launches_per_token": n_gemv,
-            "parallelism": "single GPU" if world == 1 else f"tp{world}: wqkv/w1w3 N-sharded, wo/w2 K-sharded + NCCL all-reduce",
+            "parallelism": "single GPU" if world == 1 else f"tp{world}: wqkv/w1w3 N-sharded, wo/w2 K-sharded + " + ("one-shot all-reduce fused into the GEMV epilogue (NVLink peer stores)" if a.collective == "push" else "NCCL all-reduce"),
             "l2_policy": "inputs larger than L2: every GEMV reads its own distinct weights (%.2f GB/token/GPU), streamed evict-first" % (wbytes / 1e9),
             "pdl": not a.no_pdl, "l2_prefetch_next_linear": a.l2_prefetch, "accumulate": "fp16 chains of 8 -> fp32",
         },

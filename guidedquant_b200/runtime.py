@@ -62,7 +62,7 @@ class _Lin:
 class ApGemvChain:
     def __init__(self, model: str = "llama3-8b", bits: int = 2, device=None, seed: int = 0, n_layer: int | None = None,
                  pdl: bool = True, world_size: int = 1, rank: int = 0, process_group=None, ctas_per_sm: int = 0,
-                 l2_prefetch: bool = False):
+                 l2_prefetch: bool = False, collective: str = "push"):
         self.cfg = dict(MODEL_CONFIGS[model])
         if n_layer is not None:
             self.cfg["n_layer"] = n_layer
@@ -70,6 +70,8 @@ class ApGemvChain:
         self.world, self.rank, self.pg = world_size, rank, process_group
         self.ctas = ctas_per_sm
         self.l2_prefetch = l2_prefetch
+        self.collective = collective if world_size > 1 else "none"   # "push": fused one-shot all-reduce; "nccl"
+        self.push = None
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
         self.shapes = linear_shapes(self.cfg)
         self.layers: list[list[_Lin]] = []
@@ -114,6 +116,12 @@ class ApGemvChain:
             "h2": torch.zeros((1, 1, d), dtype=torch.float16, device=self.device),
         }
         self.part = torch.zeros((1, d), dtype=torch.float32, device=self.device) if W > 1 else None
+        if self.collective == "push":
+            from .tp import PushAllReduce
+
+            # every K-sharded Linear of the chain outputs `dim` rows: 2 sites per block
+            self.push = PushAllReduce(2 * self.cfg["n_layer"], d, group=process_group, device=self.device)
+        self._site = 0
         self.hd = hd
         self.graph = None
         self.stream = torch.cuda.Stream(device=self.device)
@@ -133,7 +141,13 @@ class ApGemvChain:
         flags = _lib.APG_FLAG_PDL if self.pdl else 0
         self.launches_per_step += 1
         pf = nxt.qweight if (nxt is not None and self.l2_prefetch) else None
-        if lin.k_shard:
+        if lin.k_shard and self.push is not None:
+            site = self._site
+            self._site += 1
+            self.push.gemv_push(site, x, lin.qweight, lin.lut, lin.N, lin.K, self.bits, flags=flags)
+            self.push.finish(site, out, lin.N, flags=flags)
+            self.launches_per_step += 1
+        elif lin.k_shard:
             ap_gemv.anyprec_gemv_ex(x, out, lin.qweight, lin.lut, self.bits, flags=flags, partial=self.part,
                                     ctas_per_sm=self.ctas, prefetch_next=pf)
             torch.distributed.all_reduce(self.part, group=self.pg)
@@ -153,6 +167,7 @@ class ApGemvChain:
         b = self.buf
         x = self.x_in
         self.launches_per_step = 0
+        self._site = 0
         for li, lins in enumerate(self.layers):
             wqkv, wo, w1w3, w2 = lins
             h_out = b["h"] if li % 2 == 0 else b["h2"]

@@ -74,8 +74,9 @@ def main():
         from guidedquant_b200.runtime import ApGemvChain
 
         log("building sharded chain")
-        ch = ApGemvChain("tiny", bits=2, world_size=world, rank=rank, process_group=dist.group.WORLD)
-        log("chain built")
+        ch = ApGemvChain("tiny", bits=2, world_size=world, rank=rank, process_group=dist.group.WORLD, collective="push")
+        chn = ApGemvChain("tiny", bits=2, world_size=world, rank=rank, process_group=dist.group.WORLD, collective="nccl")
+        log("chains built")
         xh = torch.randn((1, 1, ch.cfg["dim"])).half()
         dist.broadcast(xh_dev := xh.cuda(), 0)
         y_eager = ch.eager_token(xh_dev)
@@ -87,6 +88,16 @@ def main():
         dist.all_gather(ys, y_eager)
         assert all(torch.equal(ys[0], v) for v in ys), "ranks disagree on the all-reduced output"
         assert torch.isfinite(y_eager).all() and float(y_eager.abs().max()) > 0
+        y_nccl = chn.eager_token(xh_dev)
+        torch.cuda.synchronize()
+        err = float((y_eager.float() - y_nccl.float()).abs().max() / y_nccl.float().abs().max())
+        log("push vs nccl chain max err", err)
+        assert err <= 3e-3, err   # different fp32 summation orders over a 2-block chain
+        for _ in range(5):        # replay the push graph several times: counters / expected targets advance
+            y_again = ch.step_host(xh_dev.cpu().pin_memory()).clone()
+            assert torch.equal(y_again, y_graph)
+        chn.graph = None
+        del chn
         if rank == 0:
             print("sharded ApGemvChain: graph == eager, all ranks agree", flush=True)
         # a live CUDA graph that captured NCCL kernels makes communicator teardown hang: drop it first
