@@ -96,9 +96,9 @@ def lib() -> ctypes.CDLL:
     L.apd_argmax_advance.argtypes = [vp, vp, u32, vp, vp, vp, u32, u32, vp]
     L.apg_gemv_fused_push.restype = i32
     L.apg_gemv_fused_push.argtypes = [vp, vp, vp, u32, u32, i32, vp, ctypes.c_float, i32, u32, u32,
-                                      ctypes.POINTER(vp), ctypes.POINTER(vp), vp, u32, vp]
+                                      ctypes.POINTER(vp), vp, vp, u32, vp]
     L.apg_allreduce_finish.restype = i32
-    L.apg_allreduce_finish.argtypes = [vp, vp, vp, vp, vp, u32, u32, u32, vp]
+    L.apg_allreduce_finish.argtypes = [vp, vp, vp, vp, u32, u32, u32, vp]
     L.apg_prefetch_hint.restype = i32
     L.apg_prefetch_hint.argtypes = [vp, ctypes.c_uint64]
     L.apg_round_f32_to_f16.restype = i32

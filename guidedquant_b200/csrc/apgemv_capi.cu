@@ -19,8 +19,7 @@ struct Fusion {
     const void *residual = nullptr;
     uint32_t world = 1, rank = 0;
     void *const *peer_recv = nullptr;  // host array [world] of device pointers
-    void *const *peer_flag = nullptr;  // host array [world] of device pointers
-    void *local_done = nullptr;
+    const void *epoch = nullptr;
 };
 thread_local const void *g_prefetch_ptr = nullptr;  // one-shot hint consumed by the next fast GEMV launch
 thread_local uint64_t g_prefetch_bytes = 0;
@@ -154,11 +153,9 @@ int launch_fast(const void *x, void *out, float *partial, const void *qweight, c
     p.residual = static_cast<const __half *>(fu.residual);
     p.world = fu.world;
     p.rank = fu.rank;
-    for (uint32_t i = 0; i < 8; i++) {
-        p.peer_recv[i] = (fu.world > 1 && i < fu.world) ? static_cast<float *>(fu.peer_recv[i]) : nullptr;
-        p.peer_flag[i] = (fu.world > 1 && i < fu.world) ? static_cast<uint32_t *>(fu.peer_flag[i]) : nullptr;
-    }
-    p.local_done = static_cast<uint32_t *>(fu.local_done);
+    for (uint32_t i = 0; i < 8; i++)
+        p.peer_recv[i] = (fu.world > 1 && i < fu.world) ? static_cast<uint2 *>(fu.peer_recv[i]) : nullptr;
+    p.epoch = static_cast<const uint32_t *>(fu.epoch);
     p.prefetch = static_cast<const uint8_t *>(prefetch);
     p.prefetch_bytes = (prefetch && aligned(prefetch, 16)) ? prefetch_bytes : 0;
 #define APG_FAST_CASE(CPW_, RS_) \
@@ -255,21 +252,19 @@ int apg_gemv_fused(const void *x, void *out, float *partial_f32, const void *qwe
 
 int apg_gemv_fused_push(const void *x, const void *qweight, const void *lut, uint32_t N, uint32_t K, int bits,
                         const void *norm_w, float norm_eps, int silu_mul, uint32_t world, uint32_t rank,
-                        void *const *peer_recv, void *const *peer_flag, void *local_done, uint32_t flags, void *stream) {
-    if (world < 2 || world > 8 || rank >= world || !peer_recv || !peer_flag || !local_done) return APG_ERR_MODE;
+                        void *const *peer_recv, const void *epoch, float *scratch_f32, uint32_t flags, void *stream) {
+    if (world < 2 || world > 8 || rank >= world || !peer_recv || !epoch || !scratch_f32) return APG_ERR_MODE;
     for (uint32_t i = 0; i < world; i++)
-        if (!peer_recv[i] || !peer_flag[i]) return APG_ERR_NULL;
+        if (!peer_recv[i] || !aligned(peer_recv[i], 8)) return APG_ERR_NULL;
     Fusion fu;
     fu.norm_w = norm_w, fu.eps = norm_eps, fu.silu_mul = silu_mul;
-    fu.world = world, fu.rank = rank, fu.peer_recv = peer_recv, fu.peer_flag = peer_flag, fu.local_done = local_done;
-    // the kernel needs *some* local output pointer to run its epilogue loop: slot `rank` of our own receive buffer
-    float *self = static_cast<float *>(peer_recv[rank]) + (size_t)rank * N;
-    return gemv_impl(x, nullptr, self, qweight, lut, 1, N, K, bits, flags, 0, stream, fu, true);
+    fu.world = world, fu.rank = rank, fu.peer_recv = peer_recv, fu.epoch = epoch;
+    return gemv_impl(x, nullptr, scratch_f32, qweight, lut, 1, N, K, bits, flags, 0, stream, fu, true);
 }
 
-int apg_allreduce_finish(const float *recv, const uint32_t *flag, uint32_t *expected, const void *residual, void *out,
-                         uint32_t n, uint32_t world, uint32_t flags, void *stream) {
-    if (!recv || !flag || !expected || !out) return APG_ERR_NULL;
+int apg_allreduce_finish(const void *recv, uint32_t *epoch, const void *residual, void *out, uint32_t n, uint32_t world,
+                         uint32_t flags, void *stream) {
+    if (!recv || !epoch || !out) return APG_ERR_NULL;
     if (n == 0 || world < 2 || world > 8) return APG_ERR_SHAPE;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(1);
@@ -282,7 +277,7 @@ int apg_allreduce_finish(const float *recv, const uint32_t *flag, uint32_t *expe
         cfg.attrs = attr;
         cfg.numAttrs = 1;
     }
-    APG_CUDA(cudaLaunchKernelEx(&cfg, apg::allreduce_finish_kernel, recv, flag, expected,
+    APG_CUDA(cudaLaunchKernelEx(&cfg, apg::allreduce_finish_kernel, static_cast<const uint2 *>(recv), epoch,
                                 static_cast<const __half *>(residual), static_cast<__half *>(out), n, world));
     return APG_OK;
 }

@@ -394,13 +394,13 @@ struct FastParams {
     float norm_eps;
     uint32_t act_silu_mul;   // 1: x := silu(x[0:K]) * x[K:2K] (FeedForward, model.py:261-266); x holds 2K halfs
     const __half *residual;  // != nullptr: out := fp16(y) + residual in fp16 (TransformerBlock, model.py:151-167)
-    // ---- optional fused one-shot all-reduce push (K-sharded multi-GPU path): instead of a local store,
-    // every row's fp32 partial sum is written straight into slot `rank` of EVERY peer's receive buffer over NVLink
-    // (peer_recv[p] = that peer's fp32 [world][N]); the last CTA to finish then bumps every peer's arrival counter.
+    // ---- optional fused one-shot all-reduce push (K-sharded multi-GPU path): every row's fp32 partial
+    // sum is written, together with the current epoch, as ONE 8-byte store into slot `rank` of EVERY peer's receive
+    // buffer over NVLink (peer_recv[p] = that peer's uint2 [world][N]).  Data and flag travel in the same store (the
+    // "LL" idea): no fences, no atomics, one one-way NVLink latency; the receiver polls each slot for the epoch.
     uint32_t world, rank;
-    float *peer_recv[8];
-    uint32_t *peer_flag[8];
-    uint32_t *local_done;    // this GPU's CTA-completion counter for the launch (self-resetting)
+    uint2 *peer_recv[8];
+    const uint32_t *epoch;   // device counter of this all-reduce site; the value pushed is *epoch + 1
     const uint8_t *prefetch; // optional: bytes the NEXT kernel on the stream will stream (its weights) ...
     uint64_t prefetch_bytes; // ... pulled into L2 by this kernel's producer threads while its warps compute
 };
@@ -609,6 +609,7 @@ __global__ void __launch_bounds__(544, 1) gemv_fast_kernel(const FastParams p) {
     }
 
     __syncthreads();
+    const uint32_t ep = (p.world > 1) ? (*p.epoch + 1u) : 0u;
     // fixed-order combination of the per-chunk partial sums -> deterministic results
     for (uint32_t r = threadIdx.x; r < nrows; r += blockDim.x) {
         float v = red[r * nwk];
@@ -620,19 +621,11 @@ __global__ void __launch_bounds__(544, 1) gemv_fast_kernel(const FastParams p) {
         }
         if (p.partial) p.partial[r_begin + r] = v;
         if (p.world > 1) {
+            const uint2 pkt = make_uint2(__float_as_uint(v), ep);
 #pragma unroll 1
-            for (uint32_t pr = 0; pr < p.world; pr++) p.peer_recv[pr][(size_t)p.rank * N + r_begin + r] = v;
-        }
-    }
-    if (p.world > 1) {
-        __threadfence_system();  // this thread's peer stores are visible system-wide before the CTA is counted
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            const uint32_t done = atomicAdd(p.local_done, 1u);
-            if (done == gridDim.x - 1) {  // last CTA of this GPU: every CTA's stores are ordered before its count
-                *p.local_done = 0u;
-                __threadfence_system();
-                for (uint32_t pr = 0; pr < p.world; pr++) atomicAdd_system(p.peer_flag[pr], 1u);
+            for (uint32_t pr = 0; pr < p.world; pr++) {
+                uint2 *dst = p.peer_recv[pr] + (size_t)p.rank * N + r_begin + r;
+                asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(dst), "r"(pkt.x), "r"(pkt.y) : "memory");
             }
         }
     }

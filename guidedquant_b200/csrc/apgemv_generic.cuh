@@ -135,33 +135,32 @@ __global__ void __launch_bounds__(128) dequant_kernel(const uint32_t *__restrict
     }
 }
 
-// Receiver side of the fused one-shot all-reduce: wait until all `world` ranks have pushed their fp32 partial sums
-// into recv[world][n] (arrival counter bumped once per rank and use), add them in RANK ORDER (deterministic, identical
-// on every GPU), add the optional fp16 residual and round once.  One CTA; `expected` is this use's counter target and is
-// advanced by `world` for the next graph replay.
-__global__ void __launch_bounds__(1024) allreduce_finish_kernel(const float *__restrict__ recv, const uint32_t *flag,
-                                                                uint32_t *expected, const __half *__restrict__ residual,
+// Receiver side of the fused one-shot all-reduce: every element of recv[world][n] is an 8-byte (value, epoch) packet
+// stored by the owning rank's GEMV epilogue; poll each packet until it carries this use's epoch, add the `world` values
+// in RANK ORDER (deterministic, identical on every GPU), add the optional fp16 residual and round once.  One CTA; the
+// site's epoch counter is advanced for the next graph replay after every thread has read it.
+__global__ void __launch_bounds__(1024) allreduce_finish_kernel(const uint2 *recv, uint32_t *epoch,
+                                                                const __half *__restrict__ residual,
                                                                 __half *__restrict__ out, uint32_t n, uint32_t world) {
     pdl_wait_prior_grid();
     pdl_launch_dependents();
-    __shared__ uint32_t target;
-    if (threadIdx.x == 0) {
-        const uint32_t t = *expected + world;
-        uint32_t seen;
-        do {
-            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(flag) : "memory");
-        } while ((int32_t)(seen - t) < 0);
-        *expected = t;
-        target = t;
-    }
-    __syncthreads();
+    const uint32_t ep = *epoch + 1u;
     for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
         float v = 0.f;
-        for (uint32_t r = 0; r < world; r++) v += __ldcv(recv + (size_t)r * n + i);
+        for (uint32_t r = 0; r < world; r++) {
+            const uint2 *src = recv + (size_t)r * n + i;
+            uint32_t val, tag;
+            do {
+                asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(val), "=r"(tag) : "l"(src) : "memory");
+            } while (tag != ep);
+            v += __uint_as_float(val);
+        }
         __half h = __float2half_rn(v);
         if (residual) h = __hadd(h, residual[i]);
         out[i] = h;
     }
+    __syncthreads();
+    if (threadIdx.x == 0) *epoch = ep;
 }
 
 __global__ void round_f32_to_f16_kernel(const float *__restrict__ in, __half *__restrict__ out, uint32_t n) {

@@ -25,38 +25,33 @@ class PushAllReduce:
         assert 2 <= self.world <= 8
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
         self.n_sites, self.n_max = n_sites, n_max
-        self.site_bytes = self.world * n_max * 4
-        self.flag_base = n_sites * self.site_bytes
-        total = self.flag_base + n_sites * 128  # one 128-byte line per counter
-        self.buf = symm_mem.empty(total, dtype=torch.uint8, device=self.device)
-        self.buf.zero_()
+        self.site_bytes = self.world * n_max * 8          # uint2 (value, epoch) packets [world][n_max]
+        self.buf = symm_mem.empty(n_sites * self.site_bytes, dtype=torch.uint8, device=self.device)
+        self.buf.zero_()                                   # epoch 0 everywhere: the first use pushes epoch 1
         self.hdl = symm_mem.rendezvous(self.buf, self.group)
         self.peer_base = [int(p) for p in self.hdl.buffer_ptrs]
         assert len(self.peer_base) == self.world and self.peer_base[self.rank] == self.buf.data_ptr()
-        self.expected = torch.zeros(n_sites, dtype=torch.int32, device=self.device)   # per-site counter targets
-        self.local_done = torch.zeros(n_sites, dtype=torch.int32, device=self.device)  # per-site CTA counters
+        self.epoch = torch.zeros(n_sites, dtype=torch.int32, device=self.device)     # per-site epoch counters
+        self.scratch = torch.zeros(n_max, dtype=torch.float32, device=self.device)
         torch.cuda.synchronize()
         dist.barrier(self.group)
         vp = ctypes.c_void_p
         self._recv_arr = [(vp * self.world)(*[b + s * self.site_bytes for b in self.peer_base]) for s in range(n_sites)]
-        self._flag_arr = [(vp * self.world)(*[b + self.flag_base + s * 128 for b in self.peer_base]) for s in range(n_sites)]
 
     def gemv_push(self, site: int, x, qweight, lut, N: int, K: int, bits: int, norm=None, eps: float = 1e-5,
                   silu_mul: int = 0, flags: int = 0):
-        """K-shard GEMV whose epilogue pushes the fp32 partial sums into every peer's receive slot."""
-        assert N <= self.n_max
+        """K-shard GEMV whose epilogue pushes (fp32 partial sum, epoch) packets into every peer's receive slot."""
+        assert N == self.n_max, "sites are laid out [world][n_max]"
         st = _lib.lib().apg_gemv_fused_push(
             x.data_ptr(), qweight.data_ptr(), lut.data_ptr(), N, K, bits, norm.data_ptr() if norm is not None else None,
-            eps, silu_mul, self.world, self.rank, self._recv_arr[site], self._flag_arr[site],
-            self.local_done.data_ptr() + 4 * site, flags, torch.cuda.current_stream().cuda_stream)
+            eps, silu_mul, self.world, self.rank, self._recv_arr[site], self.epoch.data_ptr() + 4 * site,
+            self.scratch.data_ptr(), flags, torch.cuda.current_stream().cuda_stream)
         _lib.check(st, "apg_gemv_fused_push")
 
     def finish(self, site: int, out, N: int, residual=None, flags: int = 0):
-        """wait for all ranks' pushes of this site, sum in rank order (+ residual), round to fp16 into `out`."""
-        base = self.peer_base[self.rank]
-        # recv layout of a site is [world][n_max]; the kernel indexes [world][N] -> require N == n_max for compactness
-        st = _lib.lib().apg_allreduce_finish(base + site * self.site_bytes, base + self.flag_base + site * 128,
-                                             self.expected.data_ptr() + 4 * site,
+        """poll all ranks' packets of this site, sum in rank order (+ residual), round to fp16 into `out`."""
+        st = _lib.lib().apg_allreduce_finish(self.peer_base[self.rank] + site * self.site_bytes,
+                                             self.epoch.data_ptr() + 4 * site,
                                              residual.data_ptr() if residual is not None else None, out.data_ptr(), N,
                                              self.world, flags, torch.cuda.current_stream().cuda_stream)
         _lib.check(st, "apg_allreduce_finish")

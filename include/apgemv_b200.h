@@ -90,20 +90,22 @@ int apg_gemv_fused(const void *x, void *out, float *partial_f32, const void *qwe
 /*
  * K-sharded multi-GPU Linear with the all-reduce FUSED into the GEMV (no NCCL on the data path).  Every rank calls
  *   apg_gemv_fused_push  : GEMV over its K shard (same optional RMSNorm / SiLU*mul prologue as apg_gemv_fused); the
- *                          epilogue stores each row's fp32 partial sum into slot `rank` of EVERY peer's receive buffer
- *                          peer_recv[p] (fp32 [world][N], peer-mapped device memory, e.g. torch symmetric memory) over
- *                          NVLink, and the last CTA bumps every peer's arrival counter peer_flag[p] (system-scope atomic).
- *   apg_allreduce_finish : one small kernel that waits for `world` arrivals on this rank's counter, adds the `world`
- *                          slots in rank order (deterministic), adds the optional fp16 residual, rounds to fp16.
- * peer_recv / peer_flag are HOST arrays of `world` device pointers; local_done is a zero-initialised device uint32 used
- * by this rank's launch only; *expected (device uint32, zero-initialised, one per all-reduce site) tracks the counter
- * target across CUDA-graph replays.  world in 2..8.  New functionality: the reference has no multi-GPU inference path.
+ *                          epilogue writes each row's fp32 partial sum TOGETHER WITH THE EPOCH as one 8-byte store into
+ *                          slot `rank` of EVERY peer's receive buffer peer_recv[p] (uint2 [world][N], peer-mapped device
+ *                          memory such as torch symmetric memory) over NVLink: data and flag travel together, so there
+ *                          are no fences or atomics and the cost is one one-way NVLink latency.
+ *   apg_allreduce_finish : one small kernel that polls this rank's `world` x N packets for the epoch, adds the `world`
+ *                          values in rank order (deterministic), adds the optional fp16 residual, rounds to fp16, and
+ *                          advances *epoch.
+ * peer_recv is a HOST array of `world` device pointers; `epoch` is a device uint32 (zero-initialised, one per all-reduce
+ * site, advanced identically on every rank) so the same CUDA graph can be replayed; scratch_f32 [N] receives the local
+ * un-rounded sums.  world in 2..8.  New functionality: the reference has no multi-GPU inference path.
  */
 int apg_gemv_fused_push(const void *x, const void *qweight, const void *lut, uint32_t N, uint32_t K, int bits,
                         const void *norm_w, float norm_eps, int silu_mul, uint32_t world, uint32_t rank,
-                        void *const *peer_recv, void *const *peer_flag, void *local_done, uint32_t flags, void *stream);
-int apg_allreduce_finish(const float *recv, const uint32_t *flag, uint32_t *expected, const void *residual, void *out,
-                         uint32_t n, uint32_t world, uint32_t flags, void *stream);
+                        void *const *peer_recv, const void *epoch, float *scratch_f32, uint32_t flags, void *stream);
+int apg_allreduce_finish(const void *recv, uint32_t *epoch, const void *residual, void *out, uint32_t n, uint32_t world,
+                         uint32_t flags, void *stream);
 
 /*
  * Optional one-shot hint (per calling thread), consumed by the NEXT apg_gemv / apg_gemv_ex launch that takes the fast
