@@ -5,6 +5,7 @@
 
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "apgemv_fast.cuh"
 #include "apgemv_generic.cuh"
@@ -67,14 +68,18 @@ template <int BITS>
 bool plan_fast(uint32_t N, uint32_t K, int ctas_per_sm, int sms, FastPlan *pl) {
     const uint32_t nchunk = (K + 1023u) / 1024u;
     if (nchunk > 32) return false;
-    pl->cpw = nchunk > 16 ? 2u : 1u;
+    static const uint32_t cpw_thresh = getenv("APG_CPW_THRESH") ? (uint32_t)atoi(getenv("APG_CPW_THRESH")) : 8u;
+    pl->cpw = nchunk > cpw_thresh ? 2u : 1u;
     pl->nwk = (nchunk + pl->cpw - 1) / pl->cpw;                  // <= 16
-    pl->groups = pl->nwk >= 8 ? 1u : (8u / pl->nwk);              // ~8 consumer warps per CTA (up to 16)
+    static const uint32_t g_mode = getenv("APG_GROUP_MODE") ? (uint32_t)atoi(getenv("APG_GROUP_MODE")) : 0u;
+    if (g_mode == 0) pl->groups = pl->nwk >= 8 ? 1u : (8u / pl->nwk);   // ~8 consumer warps per CTA
+    else pl->groups = pl->nwk <= 4 ? (8u / pl->nwk) : (pl->nwk <= 8 ? 2u : 1u);  // 5..8 chunk warps: two groups, one CTA/SM
     const uint32_t ncons = pl->groups * pl->nwk;
     pl->threads = (ncons + 1) * 32u;
     const uint32_t row_bytes = K / 8u * BITS;                     // all planes of one row
     uint32_t rs = 8;
-    while (rs > 2 && rs * row_bytes > 16u * 1024u) rs >>= 1;      // stage <= 16 KB where possible
+    static const uint32_t stage_kb = getenv("APG_STAGE_KB") ? (uint32_t)atoi(getenv("APG_STAGE_KB")) : 32u;
+    while (rs > 2 && rs * row_bytes > stage_kb * 1024u) rs >>= 1;  // stage <= 16 KB where possible
     pl->rs = rs;
     pl->stage_bytes = rs * row_bytes;
     int c = ctas_per_sm > 0 ? ctas_per_sm : (ncons <= 8 ? 2 : 1);
