@@ -39,7 +39,7 @@ def parse():
     ap.add_argument("--no-pdl", action="store_true")
     ap.add_argument("--ctas", type=int, default=0)
     ap.add_argument("--workload", default="decode", choices=["decode", "gemv-chain"],
-                    help="decode: the whole token step (1 GPU); gemv-chain: only the 4*L APLinear GEMVs (always used for N > 1)")
+                    help="decode: the whole token step (tensor-parallel for N > 1); gemv-chain: only the 4*L APLinear GEMVs")
     ap.add_argument("--max-seq", type=int, default=512)
     ap.add_argument("--collective", default="push", choices=["push", "nccl"],
                     help="N > 1: fused one-shot all-reduce pushed from the GEMV epilogue over NVLink peer memory, or NCCL")
@@ -153,7 +153,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     model = a.model or "llama3-8b"  # same workload at every N so the scaling series is comparable (70B: --model llama3-70b)
-    full_decode = a.workload == "decode" and max(world, a.gpus) == 1 and a.impl == "ours"
+    full_decode = a.workload == "decode" and a.impl == "ours"
     workload = (f"{model} {a.bits}-bit bs=1 decode, full token step: embed + L x (wqkv|attn|wo|w1w3|w2) + lm_head + greedy sample"
                 if full_decode else
                 f"{model} {a.bits}-bit bs=1 decode, ap_gemv hot path only ({'4*L' if a.layers is None else a.layers} APLinear GEMVs/token chain)")
@@ -216,7 +216,7 @@ def main():
         return dt
 
     warm = max(3, a.warmup)
-    full = (a.workload == "decode") and world == 1
+    full = a.workload == "decode"
     sampler = ClockSampler(local_rank)
     sampler.start()
 
@@ -239,11 +239,13 @@ def main():
 
     # ---------------- the whole decode step (1 GPU): embed + L blocks (5 launches each) + lm_head + greedy sample
     bytes_tok = None
+    tf = None
     if full:
         chain.graph = None
-        del chain
+        chain = None
         torch.cuda.empty_cache()
-        tf = APTransformer(model, bits=a.bits, max_seq_len=a.max_seq, pdl=not a.no_pdl, n_layer=a.layers).random_init()
+        tf = APTransformer(model, bits=a.bits, max_seq_len=a.max_seq, pdl=not a.no_pdl, n_layer=a.layers,
+                           world_size=world, rank=rank, process_group=pg).random_init()
         tf.capture()
         n_tok = min(a.steps, a.max_seq - 2)
 
@@ -267,7 +269,10 @@ def main():
         # a live CUDA graph that captured NCCL kernels makes communicator teardown hang: drop the graph, sync,
         # and leave without tearing the communicator down
         if world > 1:
-            chain.graph = None
+            if chain is not None:
+                chain.graph = None
+            if tf is not None:
+                tf.graph = None
             torch.cuda.synchronize()
             sys.stdout.flush()
             os._exit(0)
@@ -287,7 +292,7 @@ def main():
         "dtype": "f16", "data": "synthetic",
         "config": {
             "workload": workload, "bits": a.bits, "gemv_launches_per_token": n_gemv,
-            "parallelism": "single GPU" if world == 1 else f"tp{world}: wqkv/w1w3 N-sharded, wo/w2 K-sharded + " + ("one-shot all-reduce fused into the GEMV epilogue (NVLink peer stores)" if a.collective == "push" else "NCCL all-reduce"),
+            "parallelism": "single GPU" if world == 1 else f"tp{world}: wqkv/w1w3 N-sharded (heads / MLP columns), wo/w2 K-sharded + " + ("one-shot all-reduce fused into the GEMV epilogue (NVLink peer stores)" if (a.collective == "push" or full) else "NCCL all-reduce") + ("; lm_head replicated" if full else ""),
             "l2_policy": "inputs larger than L2: every GEMV reads its own distinct weights (%.2f GB/token/GPU), streamed evict-first" % (wbytes / 1e9),
             "pdl": not a.no_pdl, "l2_prefetch_next_linear": a.l2_prefetch, "accumulate": "fp16 chains of 8 -> fp32",
         },

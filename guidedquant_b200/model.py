@@ -32,7 +32,8 @@ MODEL_CONFIGS.setdefault("tiny128", dict(dim=1024, n_layer=2, n_head=8, n_kv=2, 
 
 class APTransformer:
     def __init__(self, model: str = "llama3-8b", bits: int = 2, max_seq_len: int = 256, device=None, pdl: bool = True,
-                 norm_eps: float = 1e-5, n_layer: int | None = None, attn_splits: int | None = None):
+                 norm_eps: float = 1e-5, n_layer: int | None = None, attn_splits: int | None = None,
+                 world_size: int = 1, rank: int = 0, process_group=None):
         self.cfg = dict(MODEL_CONFIGS[model])
         if n_layer is not None:
             self.cfg["n_layer"] = n_layer
@@ -43,15 +44,28 @@ class APTransformer:
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
         self.rope_base = ROPE_BASE.get(model, 10000.0)
         self.shapes = linear_shapes(c)
+        # tensor parallelism (Megatron pairing): heads / MLP columns split over `world` ranks; wo and w2
+        # are K-sharded and their all-reduce is fused into the GEMV epilogue (PushAllReduce); lm_head is replicated
+        self.world, self.rank, self.pg = world_size, rank, process_group
+        W = world_size
+        assert c["n_head"] % W == 0 and c["n_kv"] % W == 0 and c["inter"] % (128 * W) == 0 and c["dim"] % (128 * W) == 0
+        self.H_l, self.Hkv_l, self.inter_l, self.dk_l = c["n_head"] // W, c["n_kv"] // W, c["inter"] // W, c["dim"] // W
+        self.lshapes = {"wqkv": ((self.H_l + 2 * self.Hkv_l) * 128, c["dim"]), "wo": (c["dim"], self.dk_l),
+                        "w1w3": (2 * self.inter_l, c["dim"]), "w2": (c["dim"], self.inter_l)}
+        self.push = None
+        if W > 1:
+            from .tp import PushAllReduce
+
+            self.push = PushAllReduce(2 * c["n_layer"], c["dim"], group=process_group, device=self.device)
         d, dev, f16 = c["dim"], self.device, torch.float16
         self.nsplit = attn_splits if attn_splits is not None else max(1, min(32, max_seq_len // 512))
         self.sd: dict[str, torch.Tensor] = {}
         # activations / state
         self.x = torch.zeros(d, dtype=f16, device=dev)
         self.h = torch.zeros(d, dtype=f16, device=dev)
-        self.qkv = torch.zeros(self.shapes["wqkv"][0], dtype=f16, device=dev)
-        self.att = torch.zeros(d, dtype=f16, device=dev)
-        self.gu = torch.zeros(self.shapes["w1w3"][0], dtype=f16, device=dev)
+        self.qkv = torch.zeros(self.lshapes["wqkv"][0], dtype=f16, device=dev)
+        self.att = torch.zeros(self.dk_l, dtype=f16, device=dev)
+        self.gu = torch.zeros(self.lshapes["w1w3"][0], dtype=f16, device=dev)
         self.logits = torch.zeros(c["vocab"], dtype=f16, device=dev)
         self.best_val = torch.zeros(4096, dtype=torch.float32, device=dev)   # per-CTA arg-max partials of lm_head
         self.best_idx = torch.zeros(4096, dtype=torch.int32, device=dev)
@@ -60,9 +74,9 @@ class APTransformer:
         self.history = torch.zeros(max_seq_len + 1, dtype=torch.int32, device=dev)
         hd = 128
         self.inv_freq = (1.0 / (self.rope_base ** (torch.arange(0, hd, 2, dtype=torch.int64).float() / hd))).to(dev)
-        self.k_cache = [torch.zeros((c["n_kv"], max_seq_len, hd), dtype=f16, device=dev) for _ in range(c["n_layer"])]
-        self.v_cache = [torch.zeros((c["n_kv"], max_seq_len, hd), dtype=f16, device=dev) for _ in range(c["n_layer"])]
-        self.part = torch.zeros(c["n_head"] * self.nsplit * 132, dtype=torch.float32, device=dev) if self.nsplit > 1 else None
+        self.k_cache = [torch.zeros((self.Hkv_l, max_seq_len, hd), dtype=f16, device=dev) for _ in range(c["n_layer"])]
+        self.v_cache = [torch.zeros((self.Hkv_l, max_seq_len, hd), dtype=f16, device=dev) for _ in range(c["n_layer"])]
+        self.part = torch.zeros(self.H_l * self.nsplit * 132, dtype=torch.float32, device=dev) if self.nsplit > 1 else None
         self.graph = None
         self.stream = torch.cuda.Stream(device=dev)
         self.tok_host = torch.zeros(1, dtype=torch.int32).pin_memory()
@@ -89,12 +103,44 @@ class APTransformer:
             sd[f"layers.{i}.post_attention_layernorm.weight"] = (1 + 0.1 * torch.randn(c["dim"], device=dev, generator=g)).half()
         sd["norm.weight"] = (1 + 0.1 * torch.randn(c["dim"], device=dev, generator=g)).half()
         sd["output.weight"] = (torch.randn((c["vocab"], c["dim"]), device=dev, generator=g) / math.sqrt(c["dim"])).half()
+        if self.world > 1:  # every rank generated the same full model; keep this rank's shards
+            self.sd = {}
+            self.load_state_dict(sd)
         return self
 
     def load_state_dict(self, sd: dict):
+        """full (unsharded) state dict in; with world_size > 1 the Linears are sharded for this rank on the way."""
         for k, v in sd.items():
-            self.sd[k] = v.to(self.device).contiguous()
+            self.sd[k] = self._shard(k, v.to(self.device)).contiguous()
         return self
+
+    def _shard(self, name: str, t: torch.Tensor) -> torch.Tensor:
+        W, r, c = self.world, self.rank, self.cfg
+        if W == 1 or ".attention." not in name and ".feed_forward." not in name:
+            return t
+        from . import pack as packmod
+
+        H, Hkv, inter = c["n_head"], c["n_kv"], c["inter"]
+        rows_dim = 1 if name.endswith(".qweight") else 0
+        if ".wqkv." in name:   # rows: this rank's q heads, k heads, v heads (model.py:211 split order q | k | v)
+            q0, k0, v0 = 0, H * 128, (H + Hkv) * 128
+            idx = torch.cat([torch.arange(q0 + r * self.H_l * 128, q0 + (r + 1) * self.H_l * 128),
+                             torch.arange(k0 + r * self.Hkv_l * 128, k0 + (r + 1) * self.Hkv_l * 128),
+                             torch.arange(v0 + r * self.Hkv_l * 128, v0 + (r + 1) * self.Hkv_l * 128)]).to(t.device)
+            return t.index_select(rows_dim, idx)
+        if ".w1w3." in name:   # rows: this rank's gate columns then its up columns (model.py:261 split order w1 | w3)
+            idx = torch.cat([torch.arange(r * self.inter_l, (r + 1) * self.inter_l),
+                             torch.arange(inter + r * self.inter_l, inter + (r + 1) * self.inter_l)]).to(t.device)
+            return t.index_select(rows_dim, idx)
+        # wo / w2: K-sharded.  lut is per output row -> replicated; qweight is cut along K (re-packed if the cut falls
+        # inside a 1024-weight chunk, SURVEY.md §7.3-4)
+        if name.endswith(".lut"):
+            return t
+        K = t.shape[2] * 32
+        k0, k1 = r * (K // W), (r + 1) * (K // W)
+        if k0 % 1024 == 0 and (k1 % 1024 == 0 or k1 == K):
+            return t[:, :, k0 // 32:k1 // 32]
+        return torch.from_numpy(packmod.shard_k(t.cpu().numpy(), k0, k1)).to(t.device)
 
     # ------------------------------------------------------------------ accounting
     def algo_bytes_per_token(self, pos: int = 0) -> dict:
@@ -135,17 +181,27 @@ class APTransformer:
         scale = 1.0 / math.sqrt(128.0)
         for i in range(c["n_layer"]):
             p = f"layers.{i}."
-            (nq, kq), (no, ko), (ng, kg), (n2, k2) = (self.shapes[n] for n in ("wqkv", "wo", "w1w3", "w2"))
+            (nq, kq), (no, ko), (ng, kg), (n2, k2) = (self.lshapes[n] for n in ("wqkv", "wo", "w1w3", "w2"))
             self._fused(self.x, self.qkv, p + "attention.wqkv", nq, kq, norm=sd[p + "input_layernorm.weight"])
             if "attn" not in self.debug_skip:
               _lib.check(L.apd_attn_decode(self.qkv.data_ptr(), self.inv_freq.data_ptr(), self.k_cache[i].data_ptr(),
                                          self.v_cache[i].data_ptr(), self.pos.data_ptr(), self.att.data_ptr(),
-                                         self.part.data_ptr() if self.part is not None else None, c["n_head"], c["n_kv"],
+                                         self.part.data_ptr() if self.part is not None else None, self.H_l, self.Hkv_l,
                                          self.S, self.nsplit, scale, fl, st), "apd_attn_decode")
               self.launches_per_token += 1 + (1 if self.nsplit > 1 else 0)
-            self._fused(self.att, self.h, p + "attention.wo", no, ko, residual=self.x)
-            self._fused(self.h, self.gu, p + "feed_forward.w1w3", ng, kg, norm=sd[p + "post_attention_layernorm.weight"])
-            self._fused(self.gu, self.x, p + "feed_forward.w2", n2, k2, silu_mul=1, residual=self.h)
+            if self.push is None:
+                self._fused(self.att, self.h, p + "attention.wo", no, ko, residual=self.x)
+                self._fused(self.h, self.gu, p + "feed_forward.w1w3", ng, kg, norm=sd[p + "post_attention_layernorm.weight"])
+                self._fused(self.gu, self.x, p + "feed_forward.w2", n2, k2, silu_mul=1, residual=self.h)
+            else:  # K-sharded wo / w2: partial sums pushed to every peer from the GEMV epilogue, residual added by the finisher
+                self.push.gemv_push(2 * i, self.att, sd[p + "attention.wo.qweight"], sd[p + "attention.wo.lut"], no, ko,
+                                    self.bits, flags=fl)
+                self.push.finish(2 * i, self.h, no, residual=self.x, flags=fl)
+                self._fused(self.h, self.gu, p + "feed_forward.w1w3", ng, kg, norm=sd[p + "post_attention_layernorm.weight"])
+                self.push.gemv_push(2 * i + 1, self.gu, sd[p + "feed_forward.w2.qweight"], sd[p + "feed_forward.w2.lut"],
+                                    n2, k2, self.bits, silu_mul=1, eps=self.eps, flags=fl)
+                self.push.finish(2 * i + 1, self.x, n2, residual=self.h, flags=fl)
+                self.launches_per_token += 4
         if "lm_head" not in self.debug_skip:
           import ctypes
           npart = ctypes.c_uint32(0)

@@ -98,6 +98,33 @@ def main():
             assert torch.equal(y_again, y_graph)
         chn.graph = None
         del chn
+        # ---- tensor-parallel FULL decode step vs the single-GPU model built from the same full state dict
+        from guidedquant_b200.model import APTransformer
+
+        full = APTransformer("tiny128", bits=2, max_seq_len=32).random_init(seed=11)
+        sd_full = {k: v.clone() for k, v in full.sd.items()}
+        tp = APTransformer("tiny128", bits=2, max_seq_len=32, world_size=world, rank=rank, process_group=dist.group.WORLD)
+        tp.load_state_dict(sd_full)
+        full.reset(1)
+        tp.reset(1)
+        worst = 0.0
+        for pos, tok in enumerate([1, 9, 77, 5, 300, 2]):
+            for m in (full, tp):
+                m.token.fill_(tok)
+                m.step()
+                m.stream.synchronize()
+            a, b = full.logits.float(), tp.logits.float()
+            err = float((a - b).abs().max() / a.abs().max())
+            worst = max(worst, err)
+            assert err <= 1e-2, (pos, err)
+        toks_tp = tp.generate([1], 12)
+        toks_all = [None] * world
+        dist.all_gather_object(toks_all, toks_tp)
+        assert all(t == toks_all[0] for t in toks_all), "ranks generated different tokens"
+        log("TP decode vs single GPU: worst logit err", worst, "tokens", toks_tp[:8])
+        tp.graph = None
+        full.graph = None
+        del tp, full
         if rank == 0:
             print("sharded ApGemvChain: graph == eager, all ranks agree", flush=True)
         # a live CUDA graph that captured NCCL kernels makes communicator teardown hang: drop it first
