@@ -74,6 +74,8 @@ bool plan_fast(uint32_t N, uint32_t K, int ctas_per_sm, int sms, FastPlan *pl) {
     static const uint32_t g_mode = getenv("APG_GROUP_MODE") ? (uint32_t)atoi(getenv("APG_GROUP_MODE")) : 0u;
     if (g_mode == 0) pl->groups = pl->nwk >= 8 ? 1u : (8u / pl->nwk);   // ~8 consumer warps per CTA
     else pl->groups = pl->nwk <= 4 ? (8u / pl->nwk) : (pl->nwk <= 8 ? 2u : 1u);  // 5..8 chunk warps: two groups, one CTA/SM
+    static const uint32_t g_force = getenv("APG_GROUPS") ? (uint32_t)atoi(getenv("APG_GROUPS")) : 0u;
+    if (g_force && pl->nwk * g_force <= 16) pl->groups = g_force;
     const uint32_t ncons = pl->groups * pl->nwk;
     pl->threads = (ncons + 1) * 32u;
     const uint32_t row_bytes = K / 8u * BITS;                     // all planes of one row

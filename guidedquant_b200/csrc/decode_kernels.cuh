@@ -121,13 +121,27 @@ __global__ void __launch_bounds__(32 * kAttnWarps) attn_decode_kernel(
 
     for (int b = (int)(split * kAttnWarps) + w; b < nblk; b += (int)(nsplit * kAttnWarps)) {
         const int tb = b << 5, nt = min(32, pos - tb);
+        // ---- issue ALL loads of the block first: this lane's K row (phase 1) and its 8 V half-rows (phase 3), so the
+        //      block costs one memory round trip instead of two
+        uint4 kv[16];
+        if (lane < nt) {
+            const uint4 *kr4 = reinterpret_cast<const uint4 *>(Kb + (size_t)(tb + lane) * kHeadDim);
+#pragma unroll
+            for (int i = 0; i < 16; i++) kv[i] = kr4[i];
+        }
+        uint4 va[8], vb[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const int tt = 4 * u + tg;
+            va[u] = vb[u] = make_uint4(0, 0, 0, 0);
+            if (tt < nt) {
+                const uint4 *vr = reinterpret_cast<const uint4 *>(Vb + (size_t)(tb + tt) * kHeadDim + 16 * dg);
+                va[u] = vr[0], vb[u] = vr[1];
+            }
+        }
         // ---- phase 1: scores of the block
         float s = -CUDART_INF_F;
         if (lane < nt) {
-            const uint4 *kr4 = reinterpret_cast<const uint4 *>(Kb + (size_t)(tb + lane) * kHeadDim);
-            uint4 kv[16];
-#pragma unroll
-            for (int i = 0; i < 16; i++) kv[i] = kr4[i];
             float a0 = 0.f, a1 = 0.f;
 #pragma unroll
             for (int i = 0; i < 16; i++) {
@@ -159,33 +173,19 @@ __global__ void __launch_bounds__(32 * kAttnWarps) attn_decode_kernel(
         __syncwarp();
         sc[w][lane] = pe;
         __syncwarp();
-        // ---- phase 3: acc = acc * corr + P.V of the block
+        // ---- phase 3: acc = acc * corr + P.V of the block (V already in registers)
 #pragma unroll
         for (int j = 0; j < 16; j++) acc[j] *= corr;
 #pragma unroll
-        for (int hb = 0; hb < 2; hb++) {
-            uint4 va[4], vb[4];
-            float pw[4];
+        for (int u = 0; u < 8; u++) {
+            const int tt = 4 * u + tg;
+            const float pw = (tt < nt) ? sc[w][tt] : 0.f;
+            const uint32_t wv[8] = {va[u].x, va[u].y, va[u].z, va[u].w, vb[u].x, vb[u].y, vb[u].z, vb[u].w};
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const int tt = 16 * hb + 4 * u + tg;
-                pw[u] = 0.f;
-                va[u] = vb[u] = make_uint4(0, 0, 0, 0);
-                if (tt < nt) {
-                    const uint4 *vr = reinterpret_cast<const uint4 *>(Vb + (size_t)(tb + tt) * kHeadDim + 16 * dg);
-                    va[u] = vr[0], vb[u] = vr[1];
-                    pw[u] = sc[w][tt];
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const uint32_t wv[8] = {va[u].x, va[u].y, va[u].z, va[u].w, vb[u].x, vb[u].y, vb[u].z, vb[u].w};
-#pragma unroll
-                for (int j = 0; j < 8; j++) {
-                    const float2 f = __half22float2(*reinterpret_cast<const __half2 *>(&wv[j]));
-                    acc[2 * j] = fmaf(pw[u], f.x, acc[2 * j]);
-                    acc[2 * j + 1] = fmaf(pw[u], f.y, acc[2 * j + 1]);
-                }
+            for (int j = 0; j < 8; j++) {
+                const float2 f = __half22float2(*reinterpret_cast<const __half2 *>(&wv[j]));
+                acc[2 * j] = fmaf(pw, f.x, acc[2 * j]);
+                acc[2 * j + 1] = fmaf(pw, f.y, acc[2 * j + 1]);
             }
         }
     }
