@@ -1,0 +1,78 @@
+"""Checkpoint conversion: HF-named packed Any-Precision checkpoint (what any_precision/quantization/pack.py:133-203
+writes: `model.layers.{i}.self_attn.q_proj.qweight`, `...lut{b}`, ...) -> the fused gpt-fast names the decode runtime
+loads.  Mirrors the reference's inference/sqllm_llama_convert_fuse.py:12-118 (same renames, `lut{bitwidth}` selection,
+`qweight[:bitwidth]` slicing, q|k|v and gate|up concatenation along the output-row axis, bf16 -> fp16), with two
+differences: the layer count is read from the keys instead of being guessed from the directory name (the reference
+rejects everything but Llama-2 directory names, :62-69), and nothing is written unless asked.
+
+    python -m guidedquant_b200.convert --ckpt_dir <dir> --bitwidth 2      # writes <dir>/converted_pytorch_model.bin
+"""
+from __future__ import annotations
+
+import argparse
+import os
+import re
+
+import torch
+
+REPLACEMENTS = {  # sqllm_llama_convert_fuse.py:12-24
+    "embed_tokens": "tok_embeddings",
+    "self_attn": "attention",
+    "o_proj": "wo",
+    "mlp": "feed_forward",
+    "down_proj": "w2",
+    "lm_head": "output",
+    "lookup_table": "lut",
+}
+
+
+def convert_state_dict(ckpt: dict, bitwidth: int) -> dict:
+    new = {}
+    for key, value in ckpt.items():
+        k = key.replace("model.", "")
+        for old, rep in REPLACEMENTS.items():
+            k = k.replace(old, rep)
+        if "lut" in k:  # keep only lut{bitwidth}, renamed to lut (:44-49)
+            if f"lut{bitwidth}" in k:
+                k = re.sub(r"(?<=lut)[2-8]", "", k)
+            else:
+                continue
+        new[k] = value
+    for k in list(new.keys()):
+        v = new[k]
+        if v.dtype == torch.bfloat16:
+            v = v.half()
+        if k.endswith(".lut"):
+            v = v.half()
+        if "qweight" in k:
+            v = v.contiguous()[:bitwidth, :, :]  # any-precision: the first `bitwidth` planes are the model (:59-60)
+        new[k] = v
+    layers = sorted({int(m.group(1)) for m in (re.match(r"layers\.(\d+)\.", k) for k in new) if m})
+    for i in layers:
+        a, f = f"layers.{i}.attention.", f"layers.{i}.feed_forward."
+        for suffix, dim in (("qweight", 1), ("lut", 0)):
+            if a + "q_proj." + suffix in new:  # q | k | v along the output rows (:71-97)
+                new[a + "wqkv." + suffix] = torch.cat([new.pop(a + p + "_proj." + suffix) for p in ("q", "k", "v")], dim=dim)
+            if f + "gate_proj." + suffix in new:  # gate | up (:99-116)
+                new[f + "w1w3." + suffix] = torch.cat([new.pop(f + p + "_proj." + suffix) for p in ("gate", "up")], dim=dim)
+    return new
+
+
+def convert_checkpoint(ckpt_dir: str, bitwidth: int, out_name: str = "converted_pytorch_model.bin") -> str:
+    ckpt = torch.load(os.path.join(ckpt_dir, "pytorch_model.bin"), map_location="cpu", weights_only=True)
+    out = os.path.join(ckpt_dir, out_name)
+    torch.save(convert_state_dict(ckpt, bitwidth), out)
+    return out
+
+
+def load_converted(path: str, device="cuda") -> dict:
+    """the runtime-side load (generate.py:237-238: mmap + weights_only)."""
+    return torch.load(path, map_location=device, mmap=True, weights_only=True)
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--ckpt_dir", type=str, required=True)
+    ap.add_argument("--bitwidth", type=int, required=True)
+    a = ap.parse_args()
+    print(convert_checkpoint(a.ckpt_dir, a.bitwidth))

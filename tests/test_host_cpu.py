@@ -106,3 +106,28 @@ def test_shard_bounds_and_repack_exact():
             qs = P.shard_k(q, a, b)
             assert qs.shape == (bits, 5, (b - a) // 32)
             assert np.array_equal(P.unpack_indices(qs, bits), idx[:, a:b])
+
+
+def test_checkpoint_converter_matches_reference_converter():
+    """guidedquant_b200.convert vs the reference's sqllm_llama_convert_fuse.py run on the same seeded synthetic
+    checkpoint (tests/golden/convert_golden.json, made by tests/golden/make_convert_golden.py): same keys, shapes,
+    dtypes and bytes."""
+    import json
+
+    from guidedquant_b200.convert import convert_state_dict
+    from tests.convert_fixture import digest, make_hf_checkpoint
+
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "convert_golden.json")))
+    out = convert_state_dict(make_hf_checkpoint(), gold["bitwidth"])
+    assert sorted(out.keys()) == sorted(gold["tensors"].keys())
+    for k, v in out.items():
+        assert digest(v) == gold["tensors"][k], k
+    assert out["layers.0.attention.wqkv.qweight"].shape == (3, 64 + 32 + 32, 2)
+    assert out["layers.0.feed_forward.w1w3.lut"].shape == (192, 8)
+    # a float32 lut is cast to fp16 here (the reference's cast at :56-57 tests the pre-rename key and never fires)
+    f32 = make_hf_checkpoint(n_layer=1)
+    f32["model.layers.0.self_attn.o_proj.lut2"] = f32["model.layers.0.self_attn.o_proj.lut2"].float()
+    assert convert_state_dict(f32, 2)["layers.0.attention.wo.lut"].dtype == torch.float16
+    # layer count comes from the keys (the reference only accepts Llama-2 directory names)
+    small = {k: v for k, v in make_hf_checkpoint(n_layer=3).items()}
+    assert "layers.2.attention.wqkv.qweight" in convert_state_dict(small, 2)
