@@ -164,7 +164,7 @@ def main():
         tok_s, t_block, cores, steps = cpu_reference_arm(model, a.bits, a.steps, a.warmup)
         sample = f"1 block (wqkv, wo, w1w3, w2) of {model} per step, dequant->fp16 torch.matmul on CPU, value scaled by n_layer"
         line = {
-            "impl": "reference", "metric": METRIC, "value": tok_s, "unit": UNIT, "n_gpus": 0, "steps": steps, "warmup": 1,
+            "impl": "reference", "metric": METRIC, "value": tok_s, "unit": UNIT, "n_gpus": max(world, a.gpus), "steps": steps, "warmup": 1,
             "ms_per_step": t_block * 1e3, "higher_is_better": True, "scaling": "strong" if max(world, a.gpus) > 1 else "weak",
             "vs_baseline": None, "dtype": "f16", "data": "synthetic",
             "config": {"workload": workload, "reference_arm": "CPU port of APLinear.gemm (oracle/oracle.py)"},
