@@ -292,7 +292,7 @@ def main():
         "dtype": "f16", "data": "synthetic",
         "config": {
             "workload": workload, "bits": a.bits, "gemv_launches_per_token": n_gemv,
-            "parallelism": "single GPU" if world == 1 else f"tp{world}: wqkv/w1w3 N-sharded (heads / MLP columns), wo/w2 K-sharded + " + ("one-shot all-reduce fused into the GEMV epilogue (NVLink peer stores)" if (a.collective == "push" or full) else "NCCL all-reduce") + ("; lm_head replicated" if full else ""),
+            "parallelism": "single GPU" if world == 1 else f"tp{world}: wqkv/w1w3 N-sharded (heads / MLP columns), wo/w2 K-sharded + " + ("one-shot all-reduce fused into the GEMV epilogue (NVLink peer stores)" if (a.collective == "push" or full) else "NCCL all-reduce") + ("; lm_head vocab-sharded + arg-max exchange over peer memory" if full else ""),
             "l2_policy": "inputs larger than L2: every GEMV reads its own distinct weights (%.2f GB/token/GPU), streamed evict-first" % (wbytes / 1e9),
             "pdl": not a.no_pdl, "l2_prefetch_next_linear": a.l2_prefetch, "accumulate": "fp16 chains of 8 -> fp32",
         },

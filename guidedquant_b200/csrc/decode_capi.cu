@@ -52,7 +52,7 @@ int apd_attn_decode(const void *qkv, const float *inv_freq, void *k_cache, void 
 }
 
 int apd_lm_head(const void *x, const void *norm_w, float eps, const void *W, void *logits, uint32_t V, uint32_t D,
-                float *best_val, int *best_idx, uint32_t *n_partials, uint32_t flags, void *stream) {
+                float *best_val, int *best_idx, uint32_t *n_partials, uint32_t row_offset, uint32_t flags, void *stream) {
     if (!x || !norm_w || !W || !logits) return APG_ERR_NULL;
     if (V == 0 || D == 0 || D % 256 || D > 8192) return APG_ERR_SHAPE;
     if (!al(W, 16) || !al(x, 2) || !al(norm_w, 2)) return APG_ERR_ALIGN;
@@ -67,7 +67,7 @@ int apd_lm_head(const void *x, const void *norm_w, float eps, const void *W, voi
     auto go = [&](auto kern) {
         return launch(kern, dim3(grid), dim3(256), smem, flags, stream, static_cast<const __half *>(x),
                       static_cast<const __half *>(norm_w), eps, static_cast<const __half *>(W),
-                      static_cast<__half *>(logits), V, D, best_val, best_idx);
+                      static_cast<__half *>(logits), V, D, best_val, best_idx, row_offset);
     };
     switch (nv) {
         case 1: return go(apd::lm_head_kernel<1>);
@@ -86,6 +86,21 @@ int apd_argmax_advance(const float *best_val, const int *best_idx, uint32_t n, i
     if (n == 0) return APG_ERR_SHAPE;
     return launch(apd::argmax_advance_kernel, dim3(1), dim3(n >= 512 ? 1024 : 256), 0, flags, stream, best_val, best_idx, n,
                   token, pos, history, history_len);
+}
+
+int apd_argmax_advance_tp(const float *best_val, const int *best_idx, uint32_t n, uint32_t world, uint32_t rank,
+                          void *const *peer_slots, uint32_t *epoch, int *token, int *pos, int *history,
+                          uint32_t history_len, uint32_t flags, void *stream) {
+    if (!best_val || !best_idx || !token || !pos || !peer_slots || !epoch) return APG_ERR_NULL;
+    if (n == 0 || world < 2 || world > 8 || rank >= world) return APG_ERR_SHAPE;
+    uint2 *pp[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    for (uint32_t i = 0; i < world; i++) {
+        if (!peer_slots[i] || !al(peer_slots[i], 8)) return APG_ERR_ALIGN;
+        pp[i] = static_cast<uint2 *>(peer_slots[i]);
+    }
+    return launch(apd::argmax_advance_tp_kernel, dim3(1), dim3(n >= 512 ? 1024 : 256), 0, flags, stream, best_val, best_idx,
+                  n, world, rank, pp[0], pp[1], pp[2], pp[3], pp[4], pp[5], pp[6], pp[7], epoch, token, pos, history,
+                  history_len);
 }
 
 }  // extern "C"

@@ -287,7 +287,8 @@ __device__ __forceinline__ bool better(float v, int i, float bv, int bi) { retur
 template <int NV>  // NV = D / 256: uint4 loads per lane per row
 __global__ void __launch_bounds__(256) lm_head_kernel(const __half *__restrict__ x, const __half *__restrict__ norm_w, float eps,
                                                       const __half *__restrict__ W, __half *__restrict__ logits, uint32_t V,
-                                                      uint32_t D, float *__restrict__ best_val, int *__restrict__ best_idx) {
+                                                      uint32_t D, float *__restrict__ best_val, int *__restrict__ best_idx,
+                                                      uint32_t row_offset) {
     extern __shared__ __align__(16) float xs[];  // [D] normalised activations as fp32
     __shared__ float red[8];
     __shared__ int redi[8];
@@ -343,7 +344,7 @@ __global__ void __launch_bounds__(256) lm_head_kernel(const __half *__restrict__
         const __half lg = __float2half_rn(a);
         if (lane == 0) logits[row] = lg;
         const float lf = __half2float(lg);  // sampling sees the fp16 logits, like the reference (generate.py:69)
-        if (better(lf, (int)row, bv, bi)) bv = lf, bi = (int)row;
+        if (better(lf, (int)(row + row_offset), bv, bi)) bv = lf, bi = (int)(row + row_offset);
     }
     // per-CTA arg-max partial for the greedy sampler (rows ascend per warp, so ties keep the smaller index)
     if (best_val) {
@@ -398,6 +399,74 @@ __global__ void __launch_bounds__(1024) argmax_advance_kernel(const float *__res
             if (history && (uint32_t)(p + 1) < history_len) history[p + 1] = idx;
             *pos = p + 1;
         }
+    }
+}
+
+// Vocab-sharded greedy sampling (tensor parallel lm_head): every rank reduces its own arg-max partials, pushes
+// (value, epoch) and (index, epoch) packets into slot `rank` of every peer's exchange buffer over NVLink (same
+// data-with-flag scheme as the fused all-reduce), polls the `world` slots of its own buffer and picks the global winner
+// — identical on every rank (larger value, then smaller index).
+__global__ void __launch_bounds__(1024) argmax_advance_tp_kernel(const float *__restrict__ best_val, const int *__restrict__ best_idx,
+                                                                 uint32_t n, uint32_t world, uint32_t rank, uint2 *p0, uint2 *p1,
+                                                                 uint2 *p2, uint2 *p3, uint2 *p4, uint2 *p5, uint2 *p6, uint2 *p7,
+                                                                 uint32_t *epoch, int *token, int *pos, int *history,
+                                                                 uint32_t history_len) {
+    apg::pdl_wait_prior_grid();
+    apg::pdl_launch_dependents();
+    uint2 *peers[8] = {p0, p1, p2, p3, p4, p5, p6, p7};
+    __shared__ float bv[32];
+    __shared__ int bi[32];
+    float best = -CUDART_INF_F;
+    int idx = 0;
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x)
+        if (better(best_val[i], best_idx[i], best, idx)) best = best_val[i], idx = best_idx[i];
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+        if (better(ob, oi, best, idx)) best = ob, idx = oi;
+    }
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) bv[w] = best, bi[w] = idx;
+    __syncthreads();
+    if (w != 0) return;
+    best = lane < (int)(blockDim.x >> 5) ? bv[lane] : -CUDART_INF_F;
+    idx = lane < (int)(blockDim.x >> 5) ? bi[lane] : 0;
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+        if (better(ob, oi, best, idx)) best = ob, idx = oi;
+    }
+    const uint32_t ep = *epoch + 1u;
+    if (lane < (int)world) {  // lane p pushes this rank's winner to peer p
+        uint2 *dst = peers[lane] + 2 * rank;
+        asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(dst), "r"(__float_as_uint(best)), "r"(ep) : "memory");
+        asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(dst + 1), "r"((uint32_t)idx), "r"(ep) : "memory");
+    }
+    float gv = -CUDART_INF_F;
+    int gi = 0;
+    if (lane < (int)world) {  // lane r polls slot r of our own buffer
+        const uint2 *src = peers[rank] + 2 * lane;
+        uint32_t v, t0, i2, t1;
+        do {
+            asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(v), "=r"(t0) : "l"(src) : "memory");
+            asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(i2), "=r"(t1) : "l"(src + 1) : "memory");
+        } while (t0 != ep || t1 != ep);
+        gv = __uint_as_float(v), gi = (int)i2;
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, gv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, gi, o);
+        if (better(ob, oi, gv, gi)) gv = ob, gi = oi;
+    }
+    if (lane == 0) {
+        const int p = *pos;
+        *token = gi;
+        if (history && (uint32_t)(p + 1) < history_len) history[p + 1] = gi;
+        *pos = p + 1;
+        *epoch = ep;
     }
 }
 

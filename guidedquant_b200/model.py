@@ -56,7 +56,9 @@ class APTransformer:
         if W > 1:
             from .tp import PushAllReduce
 
-            self.push = PushAllReduce(2 * c["n_layer"], c["dim"], group=process_group, device=self.device)
+            # 2 all-reduce sites per block + 1 site for the arg-max exchange of the vocab-sharded lm_head
+            self.push = PushAllReduce(2 * c["n_layer"] + 1, c["dim"], group=process_group, device=self.device)
+            assert c["vocab"] % W == 0
         d, dev, f16 = c["dim"], self.device, torch.float16
         self.nsplit = attn_splits if attn_splits is not None else max(1, min(32, max_seq_len // 512))
         self.sd: dict[str, torch.Tensor] = {}
@@ -66,7 +68,8 @@ class APTransformer:
         self.qkv = torch.zeros(self.lshapes["wqkv"][0], dtype=f16, device=dev)
         self.att = torch.zeros(self.dk_l, dtype=f16, device=dev)
         self.gu = torch.zeros(self.lshapes["w1w3"][0], dtype=f16, device=dev)
-        self.logits = torch.zeros(c["vocab"], dtype=f16, device=dev)
+        self.V_l = c["vocab"] // W                      # lm_head rows of this rank (vocab-sharded under TP)
+        self.logits = torch.zeros(self.V_l, dtype=f16, device=dev)
         self.best_val = torch.zeros(4096, dtype=torch.float32, device=dev)   # per-CTA arg-max partials of lm_head
         self.best_idx = torch.zeros(4096, dtype=torch.int32, device=dev)
         self.token = torch.zeros(1, dtype=torch.int32, device=dev)
@@ -116,6 +119,8 @@ class APTransformer:
 
     def _shard(self, name: str, t: torch.Tensor) -> torch.Tensor:
         W, r, c = self.world, self.rank, self.cfg
+        if W > 1 and name == "output.weight":   # lm_head: vocab-sharded rows
+            return t[r * (c["vocab"] // W):(r + 1) * (c["vocab"] // W)]
         if W == 1 or ".attention." not in name and ".feed_forward." not in name:
             return t
         from . import pack as packmod
@@ -206,10 +211,17 @@ class APTransformer:
           import ctypes
           npart = ctypes.c_uint32(0)
           _lib.check(L.apd_lm_head(self.x.data_ptr(), sd["norm.weight"].data_ptr(), self.eps, sd["output.weight"].data_ptr(),
-                                 self.logits.data_ptr(), c["vocab"], c["dim"], self.best_val.data_ptr(),
-                                 self.best_idx.data_ptr(), ctypes.byref(npart), fl & ~self.lm_head_no_pdl, st), "apd_lm_head")
+                                 self.logits.data_ptr(), self.V_l, c["dim"], self.best_val.data_ptr(),
+                                 self.best_idx.data_ptr(), ctypes.byref(npart), self.rank * self.V_l,
+                                 fl & ~self.lm_head_no_pdl, st), "apd_lm_head")
           self._npart = npart.value
-        if "sample" not in self.debug_skip:
+        if "sample" not in self.debug_skip and self.push is not None:
+          site = 2 * c["n_layer"]
+          _lib.check(L.apd_argmax_advance_tp(self.best_val.data_ptr(), self.best_idx.data_ptr(), self._npart, self.world,
+                                           self.rank, self.push.site_ptrs(site), self.push.epoch_ptr(site),
+                                           self.token.data_ptr(), self.pos.data_ptr(), self.history.data_ptr(),
+                                           self.history.numel(), fl, st), "apd_argmax_advance_tp")
+        elif "sample" not in self.debug_skip:
           _lib.check(L.apd_argmax_advance(self.best_val.data_ptr(), self.best_idx.data_ptr(), self._npart,
                                         self.token.data_ptr(), self.pos.data_ptr(),
                                         self.history.data_ptr(), self.history.numel(), fl, st), "apd_argmax_advance")

@@ -38,6 +38,13 @@ class PushAllReduce:
         vp = ctypes.c_void_p
         self._recv_arr = [(vp * self.world)(*[b + s * self.site_bytes for b in self.peer_base]) for s in range(n_sites)]
 
+    def site_ptrs(self, site: int):
+        """host array of the peers' base pointers of a site (for exchanges other than the GEMV all-reduce)."""
+        return self._recv_arr[site]
+
+    def epoch_ptr(self, site: int) -> int:
+        return self.epoch.data_ptr() + 4 * site
+
     def gemv_push(self, site: int, x, qweight, lut, N: int, K: int, bits: int, norm=None, eps: float = 1e-5,
                   silu_mul: int = 0, flags: int = 0):
         """K-shard GEMV whose epilogue pushes (fp32 partial sum, epoch) packets into every peer's receive slot."""

@@ -27,12 +27,20 @@ int apd_attn_decode(const void *qkv, const float *inv_freq, void *k_cache, void 
  * best_val/best_idx (optional, >= 2*SMs entries each): per-CTA arg-max partials of the fp16 logits for apd_argmax_advance;
  * *n_partials (optional, host) receives how many entries were written (= the grid size). */
 int apd_lm_head(const void *x, const void *norm_w, float eps, const void *W, void *logits, uint32_t V, uint32_t D,
-                float *best_val, int *best_idx, uint32_t *n_partials, uint32_t flags, void *stream);
+                float *best_val, int *best_idx, uint32_t *n_partials, uint32_t row_offset, uint32_t flags, void *stream);
+/* row_offset: index of W's first row in the full vocabulary (0 unless lm_head is vocab-sharded): added to best_idx. */
 
 /* greedy sampling (generate.py:55-73 at temperature 0) from apd_lm_head's partials: *token = argmax(logits) (first index
  * on ties; NaN never wins); history[*pos + 1] = *token (if history != NULL and in range); *pos += 1. */
 int apd_argmax_advance(const float *best_val, const int *best_idx, uint32_t n, int *token, int *pos, int *history,
                        uint32_t history_len, uint32_t flags, void *stream);
+
+/* Vocab-sharded variant: every rank reduces its partials, pushes (value|index, epoch) packets into slot `rank` of every
+ * peer's exchange buffer peer_slots[p] (uint2 [2*world], peer-mapped memory) and polls its own buffer for all `world`
+ * winners; the global pick is identical on every rank.  *epoch: device uint32, zero-initialised, advanced per call. */
+int apd_argmax_advance_tp(const float *best_val, const int *best_idx, uint32_t n, uint32_t world, uint32_t rank,
+                          void *const *peer_slots, uint32_t *epoch, int *token, int *pos, int *history,
+                          uint32_t history_len, uint32_t flags, void *stream);
 
 #ifdef __cplusplus
 }

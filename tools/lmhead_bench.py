@@ -25,7 +25,7 @@ def timeit(fn, n=20, reps=5):
         e1.record(s); s.synchronize()
     return e0.elapsed_time(e1) / (n * reps) * 1e3
 for flags in (0, 4):
-    t = timeit(lambda: L.apd_lm_head(x.data_ptr(), nw.data_ptr(), 1e-5, W.data_ptr(), logits.data_ptr(), V, D, bv.data_ptr(), bi.data_ptr(), None, flags, torch.cuda.current_stream().cuda_stream))
+    t = timeit(lambda: L.apd_lm_head(x.data_ptr(), nw.data_ptr(), 1e-5, W.data_ptr(), logits.data_ptr(), V, D, bv.data_ptr(), bi.data_ptr(), None, 0, flags, torch.cuda.current_stream().cuda_stream))
     print(f"lm_head flags={flags}: {t:.1f} us  -> {2*V*D/t/1e3:.0f} GB/s")
 H, Hkv, S = 32, 8, 512
 qkv = torch.randn((H + 2 * Hkv) * 128, device=dev).half()
