@@ -147,6 +147,33 @@ class APTransformer:
             return t[:, :, k0 // 32:k1 // 32]
         return torch.from_numpy(packmod.shard_k(t.cpu().numpy(), k0, k1)).to(t.device)
 
+    @classmethod
+    def from_checkpoint(cls, ckpt_dir: str, bitwidth: int, max_seq_len: int = 2048, **kw) -> "APTransformer":
+        """Load a packed Any-Precision checkpoint directory as written by the reference's packer
+        (any_precision/quantization/pack.py:133-203: `pytorch_model.bin` with HF names + `config.json`), converting it
+        on the fly like inference/sqllm_llama_convert_fuse.py, or its already converted `converted_pytorch_model.bin`
+        (loaded mmap'd like generate.py:237-238).  The architecture comes from config.json, not from a name table."""
+        import json
+        import os
+
+        from .convert import convert_state_dict
+
+        hf = json.load(open(os.path.join(ckpt_dir, "config.json")))
+        name = "ckpt:" + os.path.basename(os.path.normpath(ckpt_dir))
+        MODEL_CONFIGS[name] = dict(dim=hf["hidden_size"], n_layer=hf["num_hidden_layers"], n_head=hf["num_attention_heads"],
+                                   n_kv=hf.get("num_key_value_heads", hf["num_attention_heads"]),
+                                   inter=hf["intermediate_size"], vocab=hf["vocab_size"])
+        ROPE_BASE[name] = float(hf.get("rope_theta", 10000.0))
+        m = cls(name, bits=bitwidth, max_seq_len=max_seq_len, norm_eps=float(hf.get("rms_norm_eps", 1e-5)), **kw)
+        conv = os.path.join(ckpt_dir, "converted_pytorch_model.bin")
+        if os.path.exists(conv):
+            sd = torch.load(conv, map_location="cpu", mmap=True, weights_only=True)
+        else:
+            sd = convert_state_dict(torch.load(os.path.join(ckpt_dir, "pytorch_model.bin"), map_location="cpu",
+                                               weights_only=True), bitwidth)
+        sd = {k: (v.half() if v.is_floating_point() else v) for k, v in sd.items()}
+        return m.load_state_dict(sd)
+
     # ------------------------------------------------------------------ accounting
     def algo_bytes_per_token(self, pos: int = 0) -> dict:
         c = self.cfg

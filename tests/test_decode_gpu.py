@@ -92,3 +92,40 @@ def test_generate_is_deterministic_and_graph_equals_eager():
     # prompt longer than one token (sequential prefill)
     c = m.generate([1, 5, 9], 5)
     assert c[:3] == [1, 5, 9] and len(c) == 8
+
+
+def test_from_checkpoint_roundtrip(tmp_path):
+    """HF-named packed checkpoint directory (config.json + pytorch_model.bin with lut{b} keys, 4 planes) -> from_checkpoint at
+    3 bits == the same model built from the hand-converted state dict."""
+    import json
+
+    from guidedquant_b200.convert import convert_state_dict
+    from guidedquant_b200.model import APTransformer
+
+    g = torch.Generator().manual_seed(3)
+    dim, H, Hkv, inter, vocab, L, planes = 256, 2, 1, 512, 128, 2, 4
+    hf = {"model.embed_tokens.weight": torch.randn((vocab, dim), generator=g).half(), "model.norm.weight": torch.ones(dim).half(),
+          "lm_head.weight": (torch.randn((vocab, dim), generator=g) / 16).half()}
+    for i in range(L):
+        p = f"model.layers.{i}."
+        for nm, (n, k) in {"self_attn.q_proj": (H * 128, dim), "self_attn.k_proj": (Hkv * 128, dim), "self_attn.v_proj": (Hkv * 128, dim),
+                           "self_attn.o_proj": (dim, dim), "mlp.gate_proj": (inter, dim), "mlp.up_proj": (inter, dim),
+                           "mlp.down_proj": (dim, inter)}.items():
+            hf[p + nm + ".qweight"] = torch.randint(-2**31, 2**31 - 1, (planes, n, k // 32), dtype=torch.int32, generator=g)
+            for b in (3, 4):
+                hf[p + nm + f".lut{b}"] = (torch.randn((n, 2 ** b), generator=g) * (1.6 / k ** 0.5)).half()
+        hf[p + "input_layernorm.weight"] = torch.ones(dim).half()
+        hf[p + "post_attention_layernorm.weight"] = torch.ones(dim).half()
+    d = tmp_path / "tiny-ckpt"
+    d.mkdir()
+    torch.save(hf, d / "pytorch_model.bin")
+    json.dump({"hidden_size": dim, "num_hidden_layers": L, "num_attention_heads": H, "num_key_value_heads": Hkv,
+               "intermediate_size": inter, "vocab_size": vocab, "rope_theta": 500000.0, "rms_norm_eps": 1e-5}, open(d / "config.json", "w"))
+    m = APTransformer.from_checkpoint(str(d), 3, max_seq_len=32)
+    a = m.generate([1], 10)
+    import guidedquant_b200.model as mod
+
+    mod.MODEL_CONFIGS["ckpt-ref"] = dict(dim=dim, n_layer=L, n_head=H, n_kv=Hkv, inter=inter, vocab=vocab)
+    mod.ROPE_BASE["ckpt-ref"] = 500000.0
+    m2 = APTransformer("ckpt-ref", bits=3, max_seq_len=32).load_state_dict(convert_state_dict(hf, 3))
+    assert m2.generate([1], 10) == a and len(a) == 11
