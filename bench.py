@@ -286,6 +286,13 @@ def main():
     peak, peak_src = measured_peak_gbs()
     t_chain = dt_chain / args_steps_chain  # seconds per token of the GEMV chain alone
     achieved = ab_chain / t_chain / 1e9          # GB/s per GPU of the GEMV launches (launch gaps included)
+    traffic = None                                # measured DRAM bytes per launch (ncu --set full), when recorded for this config
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_gemv_traffic.json")))
+        if world == 1 and tj.get("model") == model and tj.get("bits") == a.bits and a.layers is None:
+            traffic = tj["per_layer_bytes"] / 4.0
+    except Exception:
+        pass
     line = {
         "metric": METRIC, "value": tok_s, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": warm,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak", "vs_baseline": None,
@@ -301,7 +308,8 @@ def main():
                 "d2h_bytes_per_step": d2h},
         "gpu_launches": launches * a.steps,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src, "kernel": "apg::gemv_fast_kernel",
+                     "traffic": traffic, "traffic_note": "avg DRAM bytes per GEMV launch from profiles/r1_gemv_traffic.json (ncu --set full); algorithmic avg %.0f" % (ab_chain / n_gemv),
+                     "peak_source": peak_src, "kernel": "apg::gemv_fast_kernel",
                      "algorithmic_bytes_per_step": ab_chain, "launches_per_step": n_gemv,
                      "timed_as": "the %d GEMV launches of a token replayed as their own CUDA graph in this process: %.1f us/token" % (n_gemv, t_chain * 1e6),
                      "frac_of_8TBs": achieved / 8000.0},
