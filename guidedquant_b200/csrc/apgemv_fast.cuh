@@ -86,20 +86,14 @@ struct FastCfg;
 template <>
 struct FastCfg<2> {
     static constexpr int ROW_TBL_BYTES = 64;  // 16 x half2
-    // 2-bit: the 16-entry pair table of a row fits in ONE register per lane (lane L holds entry L & 15) and a lookup is a
-    // 16-lane-segment SHFL.IDX, which only looks at the low 4 bits of its index operand: no table in shared memory, no
-    // masking of the index words, no PRMT address formation — 55 instead of 67 instructions per 32 weights.
-    static constexpr bool REG_TABLE = true;
 };
 template <>
 struct FastCfg<3> {
     static constexpr int ROW_TBL_BYTES = 256;  // 64 x half2
-    static constexpr bool REG_TABLE = false;
 };
 template <>
 struct FastCfg<4> {
     static constexpr int ROW_TBL_BYTES = 32;  // 16 x half
-    static constexpr bool REG_TABLE = false;
 };
 template <int BITS, int RS>
 struct FastWarpTbl {
@@ -153,29 +147,34 @@ struct BatchReduce<2> {
 template <int BITS, int RS>
 struct Tables;
 
-// 2-bit: entry p = (hA hB lA lB) -> half2( C[2hA+lA], C[2hB+lB] ), A = even k (low half).  Register tables: every lane
-// fetches the 8-byte lut row of each of the RS rows (same address in all lanes: one broadcast transaction) and keeps
-// entry (lane & 15) of every row.
+// 2-bit: entry p = (hA hB lA lB) -> half2( C[2hA+lA], C[2hB+lB] ), A = even k (low half).
 template <int RS>
 struct Tables<2, RS> {
+    static constexpr int IT = (RS + 1) / 2;  // lane covers row it*2 + (lane >> 4), entry lane & 15
     struct Regs {
-        uint2 c[RS];
+        uint2 c[IT];
     };
-    __device__ __forceinline__ static void fetch(Regs &r, const __half *__restrict__ lut, uint32_t row0, uint32_t N, int) {
+    __device__ __forceinline__ static void fetch(Regs &r, const __half *__restrict__ lut, uint32_t row0, uint32_t N,
+                                                 int lane) {
 #pragma unroll
-        for (int i = 0; i < RS; i++) {
-            const uint32_t row = min(row0 + i, N - 1);
-            r.c[i] = __ldg(reinterpret_cast<const uint2 *>(lut + (size_t)row * 4));
+        for (int it = 0; it < IT; it++) {
+            const uint32_t row = min(row0 + it * 2 + (lane >> 4), N - 1);
+            r.c[it] = __ldg(reinterpret_cast<const uint2 *>(lut + (size_t)row * 4));
         }
     }
-    __device__ __forceinline__ static void build(const Regs &r, uint32_t (&T)[RS], int lane) {
+    __device__ __forceinline__ static void store(const Regs &r, uint32_t tbl, int lane) {
         const int p = lane & 15;
         const uint32_t a = ((p >> 3) & 1) * 2 + ((p >> 1) & 1), b = ((p >> 2) & 1) * 2 + (p & 1);
         const uint32_t sel = (2 * a) | ((2 * a + 1) << 4) | ((2 * b) << 8) | ((2 * b + 1) << 12);
 #pragma unroll
-        for (int i = 0; i < RS; i++) T[i] = __byte_perm(r.c[i].x, r.c[i].y, sel);
+        for (int it = 0; it < IT; it++) {
+            const int row = it * 2 + (lane >> 4);
+            if (row < RS) {
+                const uint32_t e = __byte_perm(r.c[it].x, r.c[it].y, sel);
+                asm volatile("st.shared.b32 [%0], %1;" ::"r"(tbl + row * 64 + p * 4), "r"(e) : "memory");
+            }
+        }
     }
-    __device__ __forceinline__ static void store(const Regs &, uint32_t, int) {}
 };
 
 // 3-bit: entry p = (a2 b2 a1 b1 a0 b0) -> half2( C[a], C[b] ), A = even k.
@@ -194,7 +193,6 @@ struct Tables<3, RS> {
             r.c[it] = __ldg(reinterpret_cast<const uint4 *>(lut + (size_t)row * 8));
         }
     }
-    __device__ __forceinline__ static void build(const Regs &, uint32_t (&)[RS], int) {}
     __device__ __forceinline__ static uint32_t pick(const uint4 &c, uint32_t idx) {  // half idx (0..7) -> low 16 bits
         const uint32_t lo = (idx & 4) ? c.z : c.x, hi = (idx & 4) ? c.w : c.y;     // halfs 0..3 or 4..7
         const uint32_t w = (idx & 2) ? hi : lo;
@@ -240,7 +238,6 @@ struct Tables<4, RS> {
             r.c[it] = __ldg(reinterpret_cast<const uint2 *>(lut + (size_t)row * 16) + (lane & 3));
         }
     }
-    __device__ __forceinline__ static void build(const Regs &, uint32_t (&)[RS], int) {}
     __device__ __forceinline__ static void store(const Regs &r, uint32_t tbl, int lane) {
 #pragma unroll
         for (int it = 0; it < IT; it++) {
@@ -263,22 +260,29 @@ struct WordDot;
 
 template <int ROW_OFF>
 struct WordDot<2, ROW_OFF> {
-    // `tbl` is the row's table REGISTER (entry lane & 15); every lane of the warp must call this (SHFL is convergent).
     __device__ __forceinline__ static float run(float acc, const uint32_t (&pw)[2], const uint32_t *xr, uint32_t tbl) {
         const uint32_t H = pw[0], L = pw[1];
-        // nibble m of zh = (H[4m+3] H[4m+2] L[4m+3] L[4m+2]); of zl = (H[4m+1] H[4m] L[4m+1] L[4m]): pair indices.
-        // nibble m of zh <-> k offset 28-4m (c = 3 - m/2, pair e2 = 2 (m even) / 0 (m odd)); of zl <-> e2 = 3 / 1.
+        // nibble m of zh = (H[4m+3] H[4m+2] L[4m+3] L[4m+2]); of zl = (H[4m+1] H[4m] L[4m+1] L[4m])
         const uint32_t zh = bitsel(H, L >> 2, 0xCCCCCCCCu);
         const uint32_t zl = bitsel(H << 2, L, 0xCCCCCCCCu);
+        // byte b of each word = 4 * pair index = a complete table byte offset; byte b <-> c = 3 - b
+        const uint32_t a0 = (zh << 2) & 0x3C3C3C3Cu;  // even nibbles of zh -> pair e2 = 2
+        const uint32_t a1 = (zh >> 2) & 0x3C3C3C3Cu;  // odd  nibbles of zh -> pair e2 = 0
+        const uint32_t a2 = (zl << 2) & 0x3C3C3C3Cu;  // even nibbles of zl -> pair e2 = 3
+        const uint32_t a3 = (zl >> 2) & 0x3C3C3C3Cu;  // odd  nibbles of zl -> pair e2 = 1
         uint32_t s0 = 0u, s1 = 0u;
 #pragma unroll
-        for (int m = 0; m < 8; m++) {
-            const int xb = 4 * (3 - (m >> 1));
-            // width-16 shuffle: source lane = (lane & 16) | (index & 15); the bits above the nibble are ignored
-            const uint32_t wh = __shfl_sync(0xffffffffu, tbl, (int)(zh >> (4 * m)), 16);
-            const uint32_t wl = __shfl_sync(0xffffffffu, tbl, (int)(zl >> (4 * m)), 16);
-            s0 = hfma2_u32(wh, xr[xb + ((m & 1) ? 0 : 2)], s0);
-            s1 = hfma2_u32(wl, xr[xb + ((m & 1) ? 1 : 3)], s1);
+        for (int b = 0; b < 4; b++) {
+            const int xb = 4 * (3 - b);
+            const uint32_t sel = 0x7650u | b;
+            const uint32_t w0 = lds_b32_imm<ROW_OFF>(__byte_perm(a1, tbl, sel));
+            const uint32_t w1 = lds_b32_imm<ROW_OFF>(__byte_perm(a3, tbl, sel));
+            const uint32_t w2 = lds_b32_imm<ROW_OFF>(__byte_perm(a0, tbl, sel));
+            const uint32_t w3 = lds_b32_imm<ROW_OFF>(__byte_perm(a2, tbl, sel));
+            s0 = hfma2_u32(w0, xr[xb + 0], s0);
+            s1 = hfma2_u32(w1, xr[xb + 1], s1);
+            s0 = hfma2_u32(w2, xr[xb + 2], s0);
+            s1 = hfma2_u32(w3, xr[xb + 3], s1);
         }
         return acc_add_h2(acc, hadd2_u32(s0, s1));
     }
@@ -356,18 +360,17 @@ struct WordDot<4, ROW_OFF> {
 template <int BITS, int RS, int R>
 struct RowLoop {
     __device__ __forceinline__ static void run(float (&acc)[RS], uint32_t pbase, uint32_t row_bytes, uint32_t plane_bytes,
-                                               const uint32_t *xr, uint32_t tbl, const uint32_t (&T)[RS]) {
+                                               const uint32_t *xr, uint32_t tbl) {
         uint32_t pw[BITS];
 #pragma unroll
         for (int j = 0; j < BITS; j++) pw[j] = lds_b32(pbase + j * plane_bytes);
-        acc[R] = WordDot<BITS, R * FastCfg<BITS>::ROW_TBL_BYTES>::run(acc[R], pw, xr, FastCfg<BITS>::REG_TABLE ? T[R] : tbl);
-        RowLoop<BITS, RS, R + 1>::run(acc, pbase + row_bytes, row_bytes, plane_bytes, xr, tbl, T);
+        acc[R] = WordDot<BITS, R * FastCfg<BITS>::ROW_TBL_BYTES>::run(acc[R], pw, xr, tbl);
+        RowLoop<BITS, RS, R + 1>::run(acc, pbase + row_bytes, row_bytes, plane_bytes, xr, tbl);
     }
 };
 template <int BITS, int RS>
 struct RowLoop<BITS, RS, RS> {
-    __device__ __forceinline__ static void run(float (&)[RS], uint32_t, uint32_t, uint32_t, const uint32_t *, uint32_t,
-                                               const uint32_t (&)[RS]) {}
+    __device__ __forceinline__ static void run(float (&)[RS], uint32_t, uint32_t, uint32_t, const uint32_t *, uint32_t) {}
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -509,7 +512,7 @@ __global__ void __launch_bounds__(544, 1) gemv_fast_kernel(const FastParams p) {
         pdl_wait_prior_grid();
         if (p.residual && threadIdx.x < nrows) res_pref = p.residual[r_begin + threadIdx.x];
         uint32_t xr[CPW][16];
-        bool act[CPW], warp_has[CPW];
+        bool act[CPW];
         uint32_t woff[CPW];  // byte offset of this lane's word inside a (row, plane)
         float ss = 0.f;
 #pragma unroll
@@ -517,10 +520,7 @@ __global__ void __launch_bounds__(544, 1) gemv_fast_kernel(const FastParams p) {
             const uint32_t i = wk * CPW + cc;
             const uint32_t eff = (i < nchunk) ? chunk_eff(K, i) : 0u;
             act[cc] = (uint32_t)lane < eff;
-            warp_has[cc] = eff > 0u;
-            woff[cc] = (i * 32u + min((uint32_t)lane, eff ? eff - 1u : 0u)) * 4u;  // inactive lanes re-read a valid word
-#pragma unroll
-            for (int e = 0; e < 16; e++) xr[cc][e] = 0u;
+            woff[cc] = (i * 32u + lane) * 4u;
             if (act[cc]) {
 #pragma unroll
                 for (int c = 0; c < 4; c++) {
@@ -583,16 +583,10 @@ __global__ void __launch_bounds__(544, 1) gemv_fast_kernel(const FastParams p) {
             const uint32_t rows = min((uint32_t)RS, r_end - row0);
             // tables for this stage from the prefetched codebook rows; prefetch the next stage's rows
             // (unconditional: the row index is clamped inside fetch, so no select/copy waits on the load)
-            uint32_t T[RS];
-            if (FastCfg<BITS>::REG_TABLE) {
-                Tb::build(lr, T, lane);
-                Tb::fetch(lr, p.lut, row0 + G * RS, N, lane);
-            } else {
-                __syncwarp();
-                Tb::store(lr, tbl, lane);
-                Tb::fetch(lr, p.lut, row0 + G * RS, N, lane);
-                __syncwarp();
-            }
+            __syncwarp();
+            Tb::store(lr, tbl, lane);
+            Tb::fetch(lr, p.lut, row0 + G * RS, N, lane);
+            __syncwarp();
             mbar_wait(bar_full + 8u * slot, use & 1u);
 
             const uint32_t stage = ring0 + slot * p.stage_bytes;
@@ -600,22 +594,8 @@ __global__ void __launch_bounds__(544, 1) gemv_fast_kernel(const FastParams p) {
 #pragma unroll
             for (int r = 0; r < RS; r++) acc[r] = 0.f;
 #pragma unroll
-            for (int cc = 0; cc < CPW; cc++) {
-                if (FastCfg<BITS>::REG_TABLE) {
-                    // every lane of a warp that owns this chunk runs the row loop (the lookups are warp shuffles); lanes
-                    // past the end of a tail chunk hold x = 0 and their sums are discarded
-                    if (warp_has[cc]) {
-                        float part[RS];
-#pragma unroll
-                        for (int r = 0; r < RS; r++) part[r] = 0.f;
-                        RowLoop<BITS, RS, 0>::run(part, stage + woff[cc], row_bytes, RS * row_bytes, xr[cc], tbl, T);
-#pragma unroll
-                        for (int r = 0; r < RS; r++) acc[r] += act[cc] ? part[r] : 0.f;
-                    }
-                } else if (act[cc]) {
-                    RowLoop<BITS, RS, 0>::run(acc, stage + woff[cc], row_bytes, RS * row_bytes, xr[cc], tbl, T);
-                }
-            }
+            for (int cc = 0; cc < CPW; cc++)
+                if (act[cc]) RowLoop<BITS, RS, 0>::run(acc, stage + woff[cc], row_bytes, RS * row_bytes, xr[cc], tbl);
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_empty + 8u * slot);
 
