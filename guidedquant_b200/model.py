@@ -25,9 +25,10 @@ from . import _lib
 from .runtime import MODEL_CONFIGS, gemv_algo_bytes, linear_shapes
 
 ROPE_BASE = {"llama3-8b": 500000.0, "llama3-70b": 500000.0, "llama2-7b": 10000.0, "llama2-70b": 10000.0, "tiny": 500000.0,
-             "golden-tiny": 500000.0, "tiny128": 500000.0}
+             "golden-tiny": 500000.0, "tiny128": 500000.0, "tiny128kv4": 500000.0}
 MODEL_CONFIGS.setdefault("golden-tiny", dict(dim=256, n_layer=2, n_head=2, n_kv=1, inter=512, vocab=256))
 MODEL_CONFIGS.setdefault("tiny128", dict(dim=1024, n_layer=2, n_head=8, n_kv=2, inter=2048, vocab=1024))
+MODEL_CONFIGS.setdefault("tiny128kv4", dict(dim=1024, n_layer=2, n_head=8, n_kv=4, inter=2048, vocab=1024))
 
 
 class APTransformer:
@@ -145,7 +146,7 @@ class APTransformer:
         k0, k1 = r * (K // W), (r + 1) * (K // W)
         if k0 % 1024 == 0 and (k1 % 1024 == 0 or k1 == K):
             return t[:, :, k0 // 32:k1 // 32]
-        return torch.from_numpy(packmod.shard_k(t.cpu().numpy(), k0, k1)).to(t.device)
+        return packmod.shard_k_torch(t, k0, k1)
 
     @classmethod
     def from_checkpoint(cls, ckpt_dir: str, bitwidth: int, max_seq_len: int = 2048, **kw) -> "APTransformer":

@@ -90,3 +90,29 @@ def shard_bounds(K: int, world: int, align: int = 128) -> list[tuple[int, int]]:
     units = K // align
     cuts = [(units * r) // world * align for r in range(world + 1)]
     return [(cuts[r], cuts[r + 1]) for r in range(world)]
+
+
+def shard_k_torch(qweight, k0: int, k1: int):
+    """shard_k for torch tensors on any device (used at model-shard time, where the numpy path costs seconds per
+    Linear): same contract and bit-identical results."""
+    import torch
+
+    bits, N, words = qweight.shape
+    K = words * 32
+    assert 0 <= k0 < k1 <= K and k0 % 32 == 0 and k1 % 32 == 0
+    if k0 % 1024 == 0 and (k1 % 1024 == 0 or k1 == K):
+        return qweight[:, :, k0 // 32:k1 // 32].contiguous()
+    dev = qweight.device
+    sh = (31 - torch.arange(32, device=dev, dtype=torch.int32)).view(1, 1, 1, 32)
+    # plane bits in stored (word, p) order, then scattered to k order
+    b = ((qweight.unsqueeze(-1) >> sh) & 1).to(torch.uint8).reshape(bits, N, K)
+    perm = torch.from_numpy(k_of_bit(K)).to(dev)
+    inv = torch.empty_like(perm)
+    inv[perm] = torch.arange(K, device=dev)
+    bk = b.index_select(2, inv)[:, :, k0:k1]           # [bits, N, K'] in k order
+    Kn = k1 - k0
+    permn = torch.from_numpy(k_of_bit(Kn)).to(dev)
+    bs = bk.index_select(2, permn).reshape(bits, N, Kn // 32, 32).to(torch.int64)
+    w = (bs << (31 - torch.arange(32, device=dev, dtype=torch.int64)).view(1, 1, 1, 32)).sum(dim=-1)
+    w = torch.where(w >= 2**31, w - 2**32, w)
+    return w.to(torch.int32).contiguous()

@@ -100,7 +100,7 @@ class ApGemvChain:
                     if k0 % 1024 == 0 and (k1 % 1024 == 0 or k1 == K):
                         qs = qf[:, :, k0 // 32:k1 // 32].contiguous()
                     else:  # the cut falls inside a 1024-chunk: unpack -> slice -> re-pack
-                        qs = torch.from_numpy(packmod.shard_k(qf.cpu().numpy(), k0, k1)).to(self.device)
+                        qs = packmod.shard_k_torch(qf, k0, k1)
                     lins.append(_Lin(name, N, k1 - k0, qs, lf, True))
                 del qf, lf
             self.layers.append(lins)

@@ -107,9 +107,10 @@ def main():
         # ---- tensor-parallel FULL decode step vs the single-GPU model built from the same full state dict
         from guidedquant_b200.model import APTransformer
 
-        full = APTransformer("tiny128", bits=2, max_seq_len=32).random_init(seed=11)
+        tpm = "tiny128" if world == 2 else "tiny128kv4"   # kv heads must divide by the world size
+        full = APTransformer(tpm, bits=2, max_seq_len=32).random_init(seed=11)
         sd_full = {k: v.clone() for k, v in full.sd.items()}
-        tp = APTransformer("tiny128", bits=2, max_seq_len=32, world_size=world, rank=rank, process_group=dist.group.WORLD)
+        tp = APTransformer(tpm, bits=2, max_seq_len=32, world_size=world, rank=rank, process_group=dist.group.WORLD)
         tp.load_state_dict(sd_full)
         full.reset(1)
         tp.reset(1)

@@ -106,6 +106,7 @@ def test_shard_bounds_and_repack_exact():
             qs = P.shard_k(q, a, b)
             assert qs.shape == (bits, 5, (b - a) // 32)
             assert np.array_equal(P.unpack_indices(qs, bits), idx[:, a:b])
+            assert np.array_equal(P.shard_k_torch(torch.from_numpy(q), a, b).numpy(), qs)   # torch path: bit-identical
 
 
 def test_checkpoint_converter_matches_reference_converter():
