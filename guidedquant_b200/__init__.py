@@ -6,7 +6,10 @@ Public surface (mirrors the reference's inference/ files):
     guidedquant_b200.APLinear     gpt-fast side Linear module
     guidedquant_b200.AnyPrecisionLinear  HF side Linear module (multi-precision lut{b})
     guidedquant_b200.pack         packed bit-plane layout (pack / unpack / K-shard re-pack)
-    guidedquant_b200.sharding     K-sharded (row-parallel) APLinear with one all-reduce
+    guidedquant_b200.convert      HF-named packed checkpoint -> fused gpt-fast names (sqllm_llama_convert_fuse.py)
+    guidedquant_b200.model        APTransformer: the whole decode step as one CUDA graph (single GPU or tensor parallel)
+    guidedquant_b200.runtime      ApGemvChain: the per-token chain of APLinear GEMVs (the hot path alone)
+    guidedquant_b200.tp           peer-memory plumbing of the fused one-shot all-reduce
 """
 import sys as _sys
 

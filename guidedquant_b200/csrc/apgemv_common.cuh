@@ -10,8 +10,6 @@
 
 namespace apg {
 
-constexpr int kWarp = 32;
-
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
@@ -50,23 +48,10 @@ __device__ __forceinline__ uint32_t lds_u16_imm(uint32_t addr) {
     asm volatile("ld.shared.u16 %0, [%1+%2];" : "=h"(v) : "r"(addr), "n"(IMM));
     return v;
 }
-__device__ __forceinline__ uint4 lds_v4(uint32_t addr) {
-    uint4 r;
-    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
-    return r;
-}
-__device__ __forceinline__ void sts_v4(uint32_t addr, uint4 v) {
-    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w));
-}
 
 __device__ __forceinline__ uint32_t hfma2_u32(uint32_t a, uint32_t b, uint32_t c) {
     uint32_t d;
     asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
-    return d;
-}
-__device__ __forceinline__ uint32_t hmul2_u32(uint32_t a, uint32_t b) {
-    uint32_t d;
-    asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
     return d;
 }
 __device__ __forceinline__ uint32_t hadd2_u32(uint32_t a, uint32_t b) {
@@ -83,11 +68,6 @@ __device__ __forceinline__ float acc_add_h2(float acc, uint32_t v) {
         : "+f"(acc)
         : "r"(v));
     return acc;
-}
-__device__ __forceinline__ float h2_sum_f32(uint32_t v) {
-    const __half2 h = *reinterpret_cast<const __half2 *>(&v);
-    const float2 f = __half22float2(h);
-    return f.x + f.y;
 }
 
 // Programmatic dependent launch (PDL) controls.  No-ops when the kernel was launched without the
@@ -109,13 +89,6 @@ template <int RB>
 __device__ __forceinline__ float batch_reduce(const float (&s)[RB], int lane);
 
 template <>
-__device__ __forceinline__ float batch_reduce<1>(const float (&s)[1], int) {
-    float v = s[0];
-#pragma unroll
-    for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
-template <>
 __device__ __forceinline__ float batch_reduce<2>(const float (&s)[2], int lane) {
     const bool hi = lane & 16;
     float keep = hi ? s[1] : s[0], send = hi ? s[0] : s[1];
@@ -136,14 +109,6 @@ __device__ __forceinline__ float batch_reduce<4>(const float (&s)[4], int lane) 
 #pragma unroll
     for (int o = 4; o >= 1; o >>= 1) keep += __shfl_xor_sync(0xffffffffu, keep, o);
     return keep;
-}
-template <int RB>
-__device__ __forceinline__ int batch_row_of_lane(int lane) {
-    return RB == 4 ? (lane >> 3) : (RB == 2 ? (lane >> 4) : 0);
-}
-template <int RB>
-__device__ __forceinline__ bool batch_lane_is_writer(int lane) {
-    return RB == 4 ? ((lane & 7) == 0) : (RB == 2 ? ((lane & 15) == 0) : (lane == 0));
 }
 
 }  // namespace apg
