@@ -87,7 +87,7 @@ def lib() -> ctypes.CDLL:
     L.apg_gemv_fused.argtypes = [vp, vp, vp, vp, vp, u32, u32, i32, vp, ctypes.c_float, i32, vp, u32, vp]
     f32 = ctypes.c_float
     L.apd_embed.restype = i32
-    L.apd_embed.argtypes = [vp, vp, vp, u32, u32, vp]
+    L.apd_embed.argtypes = [vp, vp, vp, u32, u32, u32, vp]
     L.apd_attn_decode.restype = i32
     L.apd_attn_decode.argtypes = [vp, vp, vp, vp, vp, vp, vp, u32, u32, u32, u32, f32, u32, vp]
     L.apd_lm_head.restype = i32

@@ -28,12 +28,12 @@ inline bool al(const void *p, uintptr_t a) { return (reinterpret_cast<uintptr_t>
 
 extern "C" {
 
-int apd_embed(const void *emb, const int *token, void *x, uint32_t dim, uint32_t flags, void *stream) {
+int apd_embed(const void *emb, const int *token, void *x, uint32_t dim, uint32_t vocab, uint32_t flags, void *stream) {
     if (!emb || !token || !x) return APG_ERR_NULL;
-    if (dim == 0 || dim % 8) return APG_ERR_SHAPE;
+    if (dim == 0 || dim % 8 || vocab == 0) return APG_ERR_SHAPE;
     if (!al(emb, 16) || !al(x, 16)) return APG_ERR_ALIGN;
     return launch(apd::embed_kernel, dim3(1), dim3(256), 0, flags, stream, static_cast<const __half *>(emb), token,
-                  static_cast<__half *>(x), dim);
+                  static_cast<__half *>(x), dim, vocab);
 }
 
 int apd_attn_decode(const void *qkv, const float *inv_freq, void *k_cache, void *v_cache, const int *pos, void *out,

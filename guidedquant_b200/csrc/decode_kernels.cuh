@@ -18,10 +18,11 @@ namespace apd {
 // x = tok_embeddings[token]   (model.py:123)
 // ------------------------------------------------------------------------------------------------------------
 __global__ void embed_kernel(const __half *__restrict__ emb, const int *__restrict__ token, __half *__restrict__ x,
-                             uint32_t dim) {
+                             uint32_t dim, uint32_t vocab) {
     apg::pdl_wait_prior_grid();
     apg::pdl_launch_dependents();  // the next kernel's weight prefetch may start now; it waits for us before reading x
-    const uint4 *src = reinterpret_cast<const uint4 *>(emb + (size_t)(*token) * dim);
+    const uint32_t tok = min((uint32_t)max(*token, 0), vocab - 1u);  // never read outside the table
+    const uint4 *src = reinterpret_cast<const uint4 *>(emb + (size_t)tok * dim);
     uint4 *dst = reinterpret_cast<uint4 *>(x);
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < dim / 8; i += gridDim.x * blockDim.x) dst[i] = src[i];
 }
@@ -77,6 +78,7 @@ __global__ void __launch_bounds__(32 * kAttnWarps) attn_decode_kernel(
     apg::pdl_wait_prior_grid();
     apg::pdl_launch_dependents();  // wo's weight stream may start while we attend; it waits for us before reading `out`
     const int pos = *pos_ptr;
+    if (pos < 0 || pos >= (int)S) return;  // cache full: never write outside it (the host API refuses to get here)
 
     // warp 0: RoPE of q and of the new k, KV append, q -> smem
     __half kr[4], vn[4];

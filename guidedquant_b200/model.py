@@ -209,7 +209,7 @@ class APTransformer:
         st = torch.cuda.current_stream().cuda_stream
         self.launches_per_token = 0
         if "embed" not in self.debug_skip:
-            _lib.check(L.apd_embed(sd["tok_embeddings.weight"].data_ptr(), self.token.data_ptr(), self.x.data_ptr(), c["dim"], fl, st), "apd_embed")
+            _lib.check(L.apd_embed(sd["tok_embeddings.weight"].data_ptr(), self.token.data_ptr(), self.x.data_ptr(), c["dim"], c["vocab"], fl, st), "apd_embed")
             self.launches_per_token += 1
         scale = 1.0 / math.sqrt(128.0)
         for i in range(c["n_layer"]):

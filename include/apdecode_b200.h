@@ -13,12 +13,13 @@
 extern "C" {
 #endif
 
-/* x[0:dim] = emb[*token, :]            tok_embeddings, model.py:123.  dim % 8 == 0. */
-int apd_embed(const void *emb, const int *token, void *x, uint32_t dim, uint32_t flags, void *stream);
+/* x[0:dim] = emb[clamp(*token, 0, vocab-1), :]            tok_embeddings, model.py:123.  dim % 8 == 0. */
+int apd_embed(const void *emb, const int *token, void *x, uint32_t dim, uint32_t vocab, uint32_t flags, void *stream);
 
 /* RoPE(q,k) + KV-cache append at *pos + softmax(q.K^T/sqrt(128)).V over t <= *pos     Attention.forward, model.py:206-236
  *   qkv fp16 [(H+2*Hkv)*128] (q|k|v, model.py:211); inv_freq fp32 [64]; k_cache/v_cache fp16 [Hkv, S, 128];
- *   out fp16 [H*128]; part_ws fp32 [H*nsplit*132] (only when nsplit > 1).  head_dim = 128, H/Hkv <= 8. */
+ *   out fp16 [H*128]; part_ws fp32 [H*nsplit*132] (only when nsplit > 1).  head_dim = 128, H/Hkv <= 8.
+ *   A position outside [0, S) makes the kernel return without touching the cache or `out`. */
 int apd_attn_decode(const void *qkv, const float *inv_freq, void *k_cache, void *v_cache, const int *pos, void *out,
                     float *part_ws, uint32_t H, uint32_t Hkv, uint32_t S, uint32_t nsplit, float scale, uint32_t flags,
                     void *stream);
