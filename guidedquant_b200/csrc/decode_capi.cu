@@ -2,6 +2,7 @@
 #include "apdecode_b200.h"
 
 #include <cuda_runtime.h>
+#include <stdlib.h>
 
 #include "apgemv_b200.h"
 #include "decode_kernels.cuh"
@@ -60,7 +61,8 @@ int apd_lm_head(const void *x, const void *norm_w, float eps, const void *W, voi
     if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
         return APG_ERR_CUDA;
     const uint32_t nv = D / 256;
-    uint32_t grid = (uint32_t)sms * 2u;
+    static const uint32_t per_sm = getenv("APD_LMHEAD_CTAS") ? (uint32_t)atoi(getenv("APD_LMHEAD_CTAS")) : 6u;  // measured on B200: 2 -> 5.1 TB/s, 4 -> 6.5, 6 -> 6.6
+    uint32_t grid = (uint32_t)sms * per_sm;
     if (grid * 8u > V) grid = (V + 7) / 8;
     if (n_partials) *n_partials = grid;
     const size_t smem = (size_t)D * sizeof(float);

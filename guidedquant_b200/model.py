@@ -71,8 +71,8 @@ class APTransformer:
         self.gu = torch.zeros(self.lshapes["w1w3"][0], dtype=f16, device=dev)
         self.V_l = c["vocab"] // W                      # lm_head rows of this rank (vocab-sharded under TP)
         self.logits = torch.zeros(self.V_l, dtype=f16, device=dev)
-        self.best_val = torch.zeros(4096, dtype=torch.float32, device=dev)   # per-CTA arg-max partials of lm_head
-        self.best_idx = torch.zeros(4096, dtype=torch.int32, device=dev)
+        self.best_val = torch.zeros(8192, dtype=torch.float32, device=dev)   # per-CTA arg-max partials of lm_head
+        self.best_idx = torch.zeros(8192, dtype=torch.int32, device=dev)
         self.token = torch.zeros(1, dtype=torch.int32, device=dev)
         self.pos = torch.zeros(1, dtype=torch.int32, device=dev)
         self.history = torch.zeros(max_seq_len + 1, dtype=torch.int32, device=dev)

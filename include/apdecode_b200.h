@@ -25,7 +25,7 @@ int apd_attn_decode(const void *qkv, const float *inv_freq, void *k_cache, void 
                     void *stream);
 
 /* logits[V] (fp16) = W[V,D] . (RMSNorm(x) * norm_w)      Transformer.forward tail, model.py:128-129.  D % 256 == 0, D <= 8192.
- * best_val/best_idx (optional, >= 2*SMs entries each): per-CTA arg-max partials of the fp16 logits for apd_argmax_advance;
+ * best_val/best_idx (optional, >= 8*SMs entries each): per-CTA arg-max partials of the fp16 logits for apd_argmax_advance;
  * *n_partials (optional, host) receives how many entries were written (= the grid size). */
 int apd_lm_head(const void *x, const void *norm_w, float eps, const void *W, void *logits, uint32_t V, uint32_t D,
                 float *best_val, int *best_idx, uint32_t *n_partials, uint32_t row_offset, uint32_t flags, void *stream);
