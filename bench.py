@@ -58,7 +58,10 @@ def measured_peak_gbs():
             d = json.load(open(p))
             for k in ("hbm_gbs", "hbm_gb_s", "hbm_GBs"):
                 if k in d:
-                    return float(d[k]), "measured (MEASURED_PEAKS.json)"
+                    v = d[k]
+                    if isinstance(v, dict):  # tolerate {"value": ..} / {"burst": ..} wrappers
+                        v = v.get("value", v.get("burst", v.get("gbs")))
+                    return float(v), "measured (MEASURED_PEAKS.json)"
         except Exception:
             pass
     return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s, MEASURED_PEAKS.json absent)"

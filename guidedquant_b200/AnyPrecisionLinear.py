@@ -35,7 +35,10 @@ class AnyPrecisionLinear(nn.Module):
             self.register_buffer("bias", torch.empty((out_features,), dtype=dtype, device=device))
         else:
             self.bias = None
-        self.output = torch.zeros((1, 1, self.out_features), dtype=torch.float16, device="cuda")
+        # the reference allocates this on 'cuda' at construction (AnyPrecisionLinear.py:55); here it is created on the
+        # first GEMV call on qweight's device, so that a skeleton can be built on the meta device — still ONE
+        # persistent tensor per module, returned by reference on every call
+        self.output = None
 
     def prune_precisions(self):
         self.qweight = self.qweight[:max(self.precisions)]
@@ -50,6 +53,8 @@ class AnyPrecisionLinear(nn.Module):
             weight = ap_gemv.anyprec_dequant(self.qweight, lut, w_bits).to(x.dtype)
             x = torch.matmul(x, weight.T)
         else:
+            if self.output is None or self.output.device != self.qweight.device:
+                self.output = torch.zeros((1, 1, self.out_features), dtype=torch.float16, device=self.qweight.device)
             anyprec_gemv(x.to(torch.float16).reshape(1, 1, -1), self.qweight, lut, self.output, w_bits)
             x = self.output.to(x.dtype).reshape(*x.shape[:-1], self.out_features)
         if self.bias is not None:

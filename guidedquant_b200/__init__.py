@@ -5,6 +5,7 @@ Public surface (mirrors the reference's inference/ files):
     guidedquant_b200.plugin       torch custom op `plugin::anyprec_gemv` + `anyprec_dequant`
     guidedquant_b200.APLinear     gpt-fast side Linear module
     guidedquant_b200.AnyPrecisionLinear  HF side Linear module (multi-precision lut{b})
+    guidedquant_b200.AnyPrecisionForCausalLM  HF side model wrapper (from_quantized / set_precision / generate)
     guidedquant_b200.pack         packed bit-plane layout (pack / unpack / K-shard re-pack)
     guidedquant_b200.convert      HF-named packed checkpoint -> fused gpt-fast names (sqllm_llama_convert_fuse.py)
     guidedquant_b200.model        APTransformer: the whole decode step as one CUDA graph (single GPU or tensor parallel)
