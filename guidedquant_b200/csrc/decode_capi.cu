@@ -105,4 +105,14 @@ int apd_argmax_advance_tp(const float *best_val, const int *best_idx, uint32_t n
                   history_len);
 }
 
+int apd_sample_topk_advance(const void *logits, uint32_t V, float temperature, uint32_t top_k,
+                            const unsigned long long *seed, int *token, int *pos, int *history, uint32_t history_len,
+                            uint32_t flags, void *stream) {
+    if (!logits || !seed || !token || !pos) return APG_ERR_NULL;
+    if (V == 0 || !(temperature >= 0.f)) return APG_ERR_SHAPE;
+    if (!al(logits, 16) || !al(seed, 8)) return APG_ERR_ALIGN;
+    return launch(apd::sample_topk_advance_kernel, dim3(1), dim3(apd::kSampleThreads), 0, flags, stream,
+                  static_cast<const __half *>(logits), V, temperature, top_k, seed, token, pos, history, history_len);
+}
+
 }  // extern "C"

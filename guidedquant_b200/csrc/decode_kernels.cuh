@@ -472,4 +472,190 @@ __global__ void __launch_bounds__(1024) argmax_advance_tp_kernel(const float *__
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// temperature / top-k sampling (logits_to_probs + multinomial_sample_one_no_sync, generate.py:55-73):
+//     l = logits / max(T, 1e-5);  pivot = k-th largest l;  l[l < pivot] = -inf;  p = softmax(l);  q_i ~ Exp(1);
+//     token = argmax_i p_i / q_i   ==   argmax_i ( l_i - log q_i )      (the softmax normaliser is common to all i)
+// One CTA.  The k-th largest value is found EXACTLY on order-preserving 16-bit keys of the fp16 logits (dividing by a
+// positive T keeps the order and keeps distinct fp16 values distinct in fp32): block max, then the elements within
+// kSampleWindow key steps of the max are collected into shared memory and the pivot is bisected there; if that window
+// holds fewer than k (or more than kSampleCap) elements the bisection runs over the whole array instead (slower, same
+// result).  Ties with the pivot are kept, like the reference's `logits < pivot` mask.  q_i = -log(u_i) with u_i from a
+// counter hash of (*seed, *pos, i) (sample_uniform below; restated in oracle/decode_oracle.py), so a replayed CUDA
+// graph draws fresh noise every token.  NaN logits are never selected.  top_k == 0 or >= V: no filter.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int kSampleThreads = 1024;
+constexpr uint32_t kSampleCap = 6144, kSampleWindow = 1024;
+
+__device__ __forceinline__ uint32_t f16_order_key(uint32_t h) {  // ascending with the value; NaN -> 0; -0 == +0
+    h &= 0xffffu;
+    if ((h & 0x7fffu) > 0x7c00u) return 0u;
+    if (h == 0x8000u) h = 0u;
+    return (h & 0x8000u) ? (~h & 0xffffu) : (h | 0x8000u);
+}
+__device__ __forceinline__ float f16_key_value(uint32_t key) {
+    const uint32_t h = (key & 0x8000u) ? (key & 0x7fffu) : (~key & 0xffffu);
+    return __half2float(__ushort_as_half((unsigned short)h));
+}
+__device__ __forceinline__ float sample_uniform(unsigned long long seed, uint32_t pos, uint32_t i) {  // in (0, 1), 23 bits
+    unsigned long long z = seed + 0x9E3779B97F4A7C15ull * ((((unsigned long long)pos) << 32) | i);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    return ((float)(uint32_t)(z >> 41) + 0.5f) * (1.0f / 8388608.0f);
+}
+
+// warp-uniform walk over logits[0:V]: every lane of every warp calls f(i, bits, valid) the same number of times
+template <typename F>
+__device__ __forceinline__ void for_each_logit(const __half *__restrict__ logits, uint32_t V, F f) {
+    const uint4 *v4 = reinterpret_cast<const uint4 *>(logits);
+    const uint32_t nv = V >> 3, lane = threadIdx.x & 31u, wbase = threadIdx.x & ~31u;
+    for (uint32_t j0 = wbase; j0 < nv; j0 += blockDim.x) {
+        const uint32_t j = j0 + lane;
+        const bool ok = j < nv;
+        uint4 q = make_uint4(0, 0, 0, 0);
+        if (ok) q = v4[j];
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            f(8u * j + 2u * e, w[e] & 0xffffu, ok);
+            f(8u * j + 2u * e + 1u, w[e] >> 16, ok);
+        }
+    }
+    for (uint32_t i0 = (nv << 3) + wbase; i0 < V; i0 += blockDim.x) {
+        const uint32_t i = i0 + lane;
+        const bool ok = i < V;
+        f(i, ok ? (uint32_t)__half_as_ushort(logits[i]) : 0u, ok);
+    }
+}
+
+__device__ __forceinline__ uint32_t block_sum_u32(uint32_t v, uint32_t *red) {  // every thread gets the total
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const uint32_t lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) red[w] = v;
+    __syncthreads();
+    uint32_t t = lane < (blockDim.x >> 5) ? red[lane] : 0u;
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    return t;
+}
+__device__ __forceinline__ uint32_t block_max_u32(uint32_t v, uint32_t *red) {
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+    const uint32_t lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) red[w] = v;
+    __syncthreads();
+    uint32_t t = lane < (blockDim.x >> 5) ? red[lane] : 0u;
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) t = max(t, __shfl_xor_sync(0xffffffffu, t, o));
+    return t;
+}
+
+__global__ void __launch_bounds__(kSampleThreads) sample_topk_advance_kernel(const __half *__restrict__ logits, uint32_t V,
+                                                                             float temperature, uint32_t top_k,
+                                                                             const unsigned long long *__restrict__ seed,
+                                                                             int *token, int *pos, int *history,
+                                                                             uint32_t history_len) {
+    apg::pdl_wait_prior_grid();
+    apg::pdl_launch_dependents();
+    __shared__ uint32_t red[32];
+    __shared__ float bv[32];
+    __shared__ int bi[32];
+    __shared__ uint32_t cand_idx[kSampleCap];
+    __shared__ unsigned short cand_key[kSampleCap];
+    __shared__ uint32_t n_cand;
+    const uint32_t lane = threadIdx.x & 31u;
+    const int p = *pos;
+    const unsigned long long sd = *seed;
+    const float t = fmaxf(temperature, 1e-5f);
+
+    uint32_t pivot = 1u, ncand = 0u;  // key 0 is NaN: never kept
+    bool use_list = false;
+    if (top_k > 0 && top_k < V) {
+        uint32_t mk = 0;
+        for_each_logit(logits, V, [&](uint32_t, uint32_t h, bool ok) {
+            if (ok) mk = max(mk, f16_order_key(h));
+        });
+        mk = block_max_u32(mk, red);
+        const uint32_t wlo = mk > kSampleWindow ? mk - kSampleWindow : 1u;
+        if (threadIdx.x == 0) n_cand = 0;
+        __syncthreads();
+        for_each_logit(logits, V, [&](uint32_t i, uint32_t h, bool ok) {
+            const uint32_t key = f16_order_key(h);
+            const bool in = ok && key >= wlo;
+            const uint32_t m = __ballot_sync(0xffffffffu, in);
+            if (m) {  // warp-aggregated append
+                const int leader = __ffs(m) - 1;
+                uint32_t base = 0;
+                if ((int)lane == leader) base = atomicAdd(&n_cand, (uint32_t)__popc(m));
+                base = __shfl_sync(0xffffffffu, base, leader);
+                const uint32_t slot = base + __popc(m & ((1u << lane) - 1u));
+                if (in && slot < kSampleCap) cand_idx[slot] = i, cand_key[slot] = (unsigned short)key;
+            }
+        });
+        __syncthreads();
+        ncand = n_cand;
+        use_list = ncand >= top_k && ncand <= kSampleCap;
+        // largest `lo` with count(key >= lo) >= top_k; the invariant holds at the start on both paths
+        uint32_t lo = use_list ? wlo : 0u, hi = mk;
+        while (lo < hi) {
+            const uint32_t mid = (lo + hi + 1u) >> 1;
+            uint32_t c = 0;
+            if (use_list) {
+                for (uint32_t j = threadIdx.x; j < ncand; j += blockDim.x) c += (uint32_t)cand_key[j] >= mid;
+            } else {
+                for_each_logit(logits, V, [&](uint32_t, uint32_t h, bool ok) { c += (ok && f16_order_key(h) >= mid) ? 1u : 0u; });
+            }
+            c = block_sum_u32(c, red);
+            if (c >= top_k) lo = mid;
+            else hi = mid - 1u;
+        }
+        pivot = max(lo, 1u);
+    }
+
+    float best = -CUDART_INF_F;
+    int idx = 0;
+    auto consider = [&](uint32_t i, uint32_t key) {
+        const float u = sample_uniform(sd, (uint32_t)p, i);
+        const float s = f16_key_value(key) / t - logf(-logf(u));
+        if (better(s, (int)i, best, idx)) best = s, idx = (int)i;
+    };
+    if (use_list) {
+        for (uint32_t j = threadIdx.x; j < ncand; j += blockDim.x)
+            if ((uint32_t)cand_key[j] >= pivot) consider(cand_idx[j], cand_key[j]);
+    } else {
+        for_each_logit(logits, V, [&](uint32_t i, uint32_t h, bool ok) {
+            const uint32_t key = f16_order_key(h);
+            if (ok && key >= pivot) consider(i, key);
+        });
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+        if (better(ob, oi, best, idx)) best = ob, idx = oi;
+    }
+    const uint32_t w = threadIdx.x >> 5;
+    if (lane == 0) bv[w] = best, bi[w] = idx;
+    __syncthreads();
+    if (w == 0) {
+        best = lane < (blockDim.x >> 5) ? bv[lane] : -CUDART_INF_F;
+        idx = lane < (blockDim.x >> 5) ? bi[lane] : 0;
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) {
+            const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+            if (better(ob, oi, best, idx)) best = ob, idx = oi;
+        }
+        if (lane == 0) {
+            *token = idx;
+            if (history && (uint32_t)(p + 1) < history_len) history[p + 1] = idx;
+            *pos = p + 1;
+        }
+    }
+}
+
 }  // namespace apd

@@ -89,6 +89,10 @@ class APTransformer:
         # ~250 us/token; it is launched as a plain stream-ordered kernel instead
         self.lm_head_no_pdl = _lib.APG_FLAG_PDL
         self.debug_skip: set[str] = set()  # profiling aid only: {"attn", "lm_head", "sample", "embed", "fusion"}
+        # sampling (generate.py:55-73): temperature 0 -> greedy arg-max kernel; > 0 -> apd_sample_topk_advance.  The seed
+        # lives in device memory so that set_sampling(seed=...) does not invalidate a captured graph.
+        self.temperature, self.top_k = 0.0, None
+        self.seed = torch.full((1,), 1234, dtype=torch.int64, device=dev)
 
     # ------------------------------------------------------------------ weights
     def random_init(self, seed: int = 0):
@@ -249,6 +253,10 @@ class APTransformer:
                                            self.rank, self.push.site_ptrs(site), self.push.epoch_ptr(site),
                                            self.token.data_ptr(), self.pos.data_ptr(), self.history.data_ptr(),
                                            self.history.numel(), fl, st), "apd_argmax_advance_tp")
+        elif "sample" not in self.debug_skip and self.temperature > 0.0:
+          _lib.check(L.apd_sample_topk_advance(self.logits.data_ptr(), self.V_l, float(self.temperature), int(self.top_k or 0),
+                                             self.seed.data_ptr(), self.token.data_ptr(), self.pos.data_ptr(),
+                                             self.history.data_ptr(), self.history.numel(), fl, st), "apd_sample_topk_advance")
         elif "sample" not in self.debug_skip:
           _lib.check(L.apd_argmax_advance(self.best_val.data_ptr(), self.best_idx.data_ptr(), self._npart,
                                         self.token.data_ptr(), self.pos.data_ptr(),
@@ -256,6 +264,19 @@ class APTransformer:
         self.launches_per_token += 2
 
     # ------------------------------------------------------------------ graph + generation
+    def set_sampling(self, temperature: float = 0.0, top_k: int | None = None, seed: int | None = None):
+        """temperature / top_k of the reference's sample() (generate.py:55-73).  temperature 0 (the reference CLI default,
+        generate.py:400) keeps the greedy kernel.  Changing temperature / top_k drops the captured graph; a new seed does not."""
+        if temperature > 0.0 and self.world > 1:
+            raise NotImplementedError("temperature sampling needs the full logits; lm_head is vocab-sharded under tensor parallelism")
+        if (float(temperature), top_k) != (self.temperature, self.top_k):
+            self.temperature, self.top_k, self.graph = float(temperature), top_k, None
+        if seed is not None:
+            with torch.cuda.stream(self.stream):
+                self.seed.fill_(int(seed))
+            self.stream.synchronize()
+        return self
+
     def capture(self):
         with torch.cuda.device(self.device):
             s = self.stream
@@ -299,10 +320,15 @@ class APTransformer:
         return int(self.tok_host[0])
 
     @torch.no_grad()
-    def generate(self, prompt: list[int], max_new_tokens: int) -> list[int]:
-        """greedy generation (the reference's generate(), generate.py:146-186, with a sequential prefill: prompts are
-        BOS-only in the reference's benchmark protocol, generate.py:310-313)."""
+    def generate(self, prompt: list[int], max_new_tokens: int, temperature: float | None = None, top_k: int | None = None,
+                 seed: int | None = None) -> list[int]:
+        """the reference's generate() (generate.py:146-186) with a sequential prefill (prompts are BOS-only in the
+        reference's benchmark protocol, generate.py:310-313).  Greedy unless a temperature > 0 is given / was set."""
         assert len(prompt) >= 1 and len(prompt) + max_new_tokens <= self.S
+        if temperature is not None:
+            self.set_sampling(temperature, top_k, seed)
+        elif seed is not None:
+            self.set_sampling(self.temperature, self.top_k, seed)
         self.reset(prompt[0])
         for t in prompt[1:]:  # teacher-forced prefill, one token at a time
             self.step()

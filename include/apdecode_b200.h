@@ -43,6 +43,16 @@ int apd_argmax_advance_tp(const float *best_val, const int *best_idx, uint32_t n
                           void *const *peer_slots, uint32_t *epoch, int *token, int *pos, int *history,
                           uint32_t history_len, uint32_t flags, void *stream);
 
+/* temperature / top-k sampling (logits_to_probs + multinomial_sample_one_no_sync, generate.py:55-73) on the fp16 logits
+ * of apd_lm_head: *token = argmax_i( logits[i]/max(T,1e-5) - log q_i ) over the top_k largest logits (ties with the k-th
+ * kept, like the reference's `logits < pivot` mask; top_k == 0 or >= V: no filter), q_i = -log(u_i), u_i a counter hash
+ * of (*seed, *pos, i) - a fixed documented stream, not torch's Philox (restated in oracle/decode_oracle.py).  Then
+ * history[*pos + 1] = *token and *pos += 1 like apd_argmax_advance.  seed: device uint64; logits 16-byte aligned.
+ * Single GPU (a vocab-sharded lm_head has no global top-k). */
+int apd_sample_topk_advance(const void *logits, uint32_t V, float temperature, uint32_t top_k,
+                            const unsigned long long *seed, int *token, int *pos, int *history, uint32_t history_len,
+                            uint32_t flags, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

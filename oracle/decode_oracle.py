@@ -82,3 +82,48 @@ class DecodeOracle:
     @staticmethod
     def greedy(logits: torch.Tensor) -> int:  # generate.py:55-73 with temperature 0 == argmax
         return int(torch.argmax(logits))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# temperature / top-k sampling (generate.py:55-73) — oracle of apd_sample_topk_advance
+# ---------------------------------------------------------------------------------------------------------------------
+def sample_uniform(seed: int, pos: int, n: int):
+    """u_i in (0,1), i < n: the documented counter hash of the kernel (decode_kernels.cuh sample_uniform), in numpy uint64."""
+    import numpy as np
+
+    with np.errstate(over="ignore"):
+        ctr = (np.uint64(pos) << np.uint64(32)) | np.arange(n, dtype=np.uint64)
+        z = np.uint64(seed) + np.uint64(0x9E3779B97F4A7C15) * ctr
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    return ((z >> np.uint64(41)).astype(np.float64) + 0.5) / 8388608.0
+
+
+def sample_topk_reference(logits_f16, temperature: float, top_k, q):
+    """The reference's own formulation, line by line (logits_to_probs + multinomial_sample_one_no_sync, generate.py:55-73),
+    with the Exp(1) noise `q` passed in instead of drawn from torch's generator."""
+    logits = torch.as_tensor(logits_f16).float()[None, :]
+    logits = logits / max(temperature, 1e-5)
+    if top_k is not None:
+        v, _ = torch.topk(logits, min(top_k, logits.size(-1)))
+        pivot = v.select(-1, -1).unsqueeze(-1)
+        logits = torch.where(logits < pivot, -float("Inf"), logits)
+    probs = torch.nn.functional.softmax(logits, dim=-1)
+    return int(torch.argmax(probs / torch.as_tensor(q, dtype=torch.float32)[None, :], dim=-1)), probs[0]
+
+
+def sample_topk_scores(logits_f16, temperature: float, top_k, seed: int, pos: int):
+    """float64 scores l_i/T - log q_i (-inf outside the top-k, ties with the k-th kept); argmax == the sampled token.
+    Equal to sample_topk_reference in exact arithmetic: softmax's normaliser is common to every i."""
+    import numpy as np
+
+    l = np.asarray(logits_f16, dtype=np.float16).astype(np.float64)
+    n = l.shape[0]
+    s = l / max(temperature, 1e-5)
+    if top_k is not None and 0 < top_k < n:
+        pivot = np.sort(l[~np.isnan(l)])[::-1][min(top_k, n) - 1] if np.count_nonzero(~np.isnan(l)) >= top_k else -np.inf
+        s = np.where(l < pivot, -np.inf, s)
+    s = np.where(np.isnan(l), -np.inf, s)
+    q = -np.log(sample_uniform(seed, pos, n))
+    return s - np.log(q), q

@@ -129,3 +129,112 @@ def test_from_checkpoint_roundtrip(tmp_path):
     mod.ROPE_BASE["ckpt-ref"] = 500000.0
     m2 = APTransformer("ckpt-ref", bits=3, max_seq_len=32).load_state_dict(convert_state_dict(hf, 3))
     assert m2.generate([1], 10) == a and len(a) == 11
+
+
+# ------------------------------------------------------------------------------------------------ temperature / top-k
+def _sample(logits_np, temperature, top_k, seed, pos, hist_len=64):
+    from guidedquant_b200 import _lib
+
+    L = _lib.lib()
+    lg = torch.from_numpy(np.asarray(logits_np, dtype=np.float16)).cuda()
+    sd = torch.tensor([seed], dtype=torch.int64, device="cuda")
+    tok = torch.full((1,), -7, dtype=torch.int32, device="cuda")
+    p = torch.tensor([pos], dtype=torch.int32, device="cuda")
+    hist = torch.zeros(hist_len, dtype=torch.int32, device="cuda")
+    _lib.check(L.apd_sample_topk_advance(lg.data_ptr(), lg.numel(), float(temperature), int(top_k or 0), sd.data_ptr(),
+                                         tok.data_ptr(), p.data_ptr(), hist.data_ptr(), hist.numel(), 0,
+                                         torch.cuda.current_stream().cuda_stream), "apd_sample_topk_advance")
+    torch.cuda.synchronize()
+    assert int(p[0]) == pos + 1
+    if pos + 1 < hist_len:
+        assert int(hist[pos + 1]) == int(tok[0])
+    return int(tok[0])
+
+
+def _check_pick(logits, temperature, top_k, seed, pos):
+    from oracle.decode_oracle import sample_topk_scores
+
+    tok = _sample(logits, temperature, top_k, seed, pos)
+    s, _ = sample_topk_scores(logits, temperature, top_k, seed, pos)
+    assert 0 <= tok < len(logits) and np.isfinite(s[tok]), (tok, "picked a token outside the top-k set")
+    # the kernel's logf differs from float64 log by a few ulp: the pick must be the oracle's arg-max or tie with it
+    assert s[tok] >= s.max() - 1e-4 * max(1.0, abs(s.max())), (tok, int(np.argmax(s)), s[tok], s.max())
+    return tok
+
+
+@pytest.mark.parametrize("V,top_k,temperature", [(128256, 32, 0.8), (128256, 200, 1.0), (1000, 200, 0.8), (4099, 7, 0.3),
+                                                 (513, None, 1.0), (64, 64, 1.0), (64, 100, 2.0), (9, 1, 1.0)])
+def test_sample_topk_matches_oracle(V, top_k, temperature):
+    rng = np.random.default_rng(V + (top_k or 0))
+    logits = (rng.standard_normal(V) * 2.5).astype(np.float16)
+    picks = {_check_pick(logits, temperature, top_k, seed=1234, pos=pos) for pos in range(6)}
+    if top_k == 1:
+        assert picks == {int(np.argmax(logits.astype(np.float32)))}
+
+
+def test_sample_topk_edge_distributions():
+    rng = np.random.default_rng(5)
+    V = 20000
+    # flat: every element ties with the pivot -> all kept (reference masks `logits < pivot` only); candidate list overflows
+    for pos in range(3):
+        _check_pick(np.full(V, 1.5, dtype=np.float16), 1.0, 32, 7, pos)
+    # wide spread: fewer than k elements inside the key window -> whole-array bisection
+    wide = np.linspace(-60000, 60000, V).astype(np.float16)
+    rng.shuffle(wide)
+    for pos in range(3):
+        _check_pick(wide, 5000.0, 6000, 7, pos)
+        _check_pick(wide, 5000.0, 50, 7, pos)
+    # tight cluster: more elements inside the window than the shared-memory list holds -> whole-array bisection
+    tight = (10.0 + 0.01 * rng.standard_normal(V)).astype(np.float16)
+    for pos in range(3):
+        _check_pick(tight, 0.05, 32, 11, pos)
+    # NaN / inf never selected / handled
+    l = (rng.standard_normal(V)).astype(np.float16)
+    l[::7] = np.nan
+    l[1::7] = -np.inf
+    for pos in range(3):
+        tok = _check_pick(l, 1.0, 40, 9, pos)
+        assert np.isfinite(l[tok])
+    # temperature 0 is clamped to 1e-5 like the reference: effectively greedy
+    l = (rng.standard_normal(V)).astype(np.float16)
+    l[123] = 9.0
+    assert _sample(l, 0.0, 32, 1, 0) == 123
+
+
+def test_sample_topk_distribution():
+    """4096 draws (the kernel advances *pos itself, so every launch uses a fresh noise counter) follow softmax(top-k)."""
+    from guidedquant_b200 import _lib
+
+    L = _lib.lib()
+    V, k, T, n = 16, 5, 0.7, 4096
+    logits = np.array([0.1, 2.0, -1.0, 1.5, 0.3, 1.9, -3.0, 0.0, 1.0, 0.5, -0.5, 2.2, 0.7, -2.0, 1.2, 0.9], dtype=np.float16)
+    lg = torch.from_numpy(logits).cuda()
+    sd = torch.tensor([42], dtype=torch.int64, device="cuda")
+    tok = torch.zeros(1, dtype=torch.int32, device="cuda")
+    p = torch.zeros(1, dtype=torch.int32, device="cuda")
+    hist = torch.zeros(n + 1, dtype=torch.int32, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    for _ in range(n):
+        _lib.check(L.apd_sample_topk_advance(lg.data_ptr(), V, T, k, sd.data_ptr(), tok.data_ptr(), p.data_ptr(),
+                                             hist.data_ptr(), hist.numel(), 0, st), "apd_sample_topk_advance")
+    torch.cuda.synchronize()
+    assert int(p[0]) == n
+    draws = hist[1:].cpu().numpy()
+    l = logits.astype(np.float64) / T
+    keep = l >= np.sort(l)[::-1][k - 1]
+    pr = np.where(keep, np.exp(l - l.max()), 0.0)
+    pr /= pr.sum()
+    freq = np.bincount(draws, minlength=V) / n
+    assert np.all(freq[~keep] == 0)
+    assert np.all(np.abs(freq - pr) <= 4.5 * np.sqrt(pr * (1 - pr) / n) + 1e-3), (freq, pr)
+
+
+def test_generate_with_temperature():
+    m, _, cfg = _build("golden-tiny", 2, 48, seed=21)
+    greedy = m.generate([1], 20)
+    a = m.generate([1], 20, temperature=1.5, top_k=50, seed=7)
+    b = m.generate([1], 20, seed=7)            # same seed, same graph -> same draw
+    c = m.generate([1], 20, seed=8)
+    assert a == b and len(a) == 21 and all(0 <= t < cfg["vocab"] for t in a)
+    assert a != c                              # the seed matters: noise is actually applied
+    assert m.generate([1], 20, temperature=0.0) == greedy

@@ -36,3 +36,26 @@ def test_decode_oracle_half_rounding_stays_close():
         logits = o.step(int(tok), pos).numpy()
         ref = g["logits"][pos]
         assert np.abs(logits - ref).max() <= 2e-2 * np.abs(ref).max(), pos
+
+
+def test_sampling_oracle_equals_reference_formulation():
+    """oracle.sample_topk_scores (what the GPU tests check the kernel against) picks the same token as the reference's
+    logits_to_probs + multinomial_sample_one_no_sync (generate.py:55-73) given the same Exp(1) noise."""
+    import numpy as np
+
+    from oracle.decode_oracle import sample_topk_reference, sample_topk_scores, sample_uniform
+
+    rng = np.random.default_rng(0)
+    u = sample_uniform(1234, 5, 200000)
+    assert 0.0 < u.min() and u.max() < 1.0 and abs(u.mean() - 0.5) < 5e-3 and abs(np.var(u) * 12 - 1) < 2e-2
+    assert not np.array_equal(u[:100], sample_uniform(1234, 6, 100)) and not np.array_equal(u[:100], sample_uniform(1235, 5, 100))
+    for t in range(100):
+        V = int(rng.integers(40, 3000))
+        l = (rng.standard_normal(V) * 2).astype(np.float16)
+        for top_k in (None, 1, 32, V + 5):
+            s, q = sample_topk_scores(l, 0.8, top_k, 99, t)
+            a, probs = sample_topk_reference(l, 0.8, top_k, q)
+            assert a == int(np.argmax(s))
+            assert np.array_equal(np.isfinite(s), (probs > 0).numpy() | np.isfinite(s))  # kept set ⊇ non-zero probs
+            if top_k is not None and top_k < V:
+                assert np.isfinite(s).sum() >= top_k
