@@ -56,6 +56,7 @@ def main():
     ap.add_argument("--rot-mb", type=int, default=512)
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "microbench.jsonl"))
     ap.add_argument("--no-ref", action="store_true")
+    ap.add_argument("--M", type=int, default=1, help="batch rows (1..8); M > 1 and bits > 4 run the generic kernel")
     a = ap.parse_args()
     os.makedirs(os.path.dirname(a.out), exist_ok=True)
     dev = torch.device("cuda:0")
@@ -69,10 +70,10 @@ def main():
             qs = [torch.randint(-2**31, 2**31 - 1, (bits, N, K // 32), dtype=torch.int32, device=dev, generator=g)
                   for _ in range(nrot)]
             lut = (torch.randn((N, 1 << bits), device=dev, generator=g) * 0.02).half()
-            x = torch.randn((1, 1, K), device=dev, generator=g).half()
-            out = torch.zeros((1, 1, N), dtype=torch.float16, device=dev)
-            ab = algo_bytes(N, K, bits)
-            rec = {"shape": name, "N": N, "K": K, "bits": bits, "algo_bytes": ab, "nrot": nrot}
+            x = torch.randn((a.M, 1, K), device=dev, generator=g).half()
+            out = torch.zeros((a.M, 1, N), dtype=torch.float16, device=dev)
+            ab = algo_bytes(N, K, bits, a.M)
+            rec = {"shape": name, "N": N, "K": K, "bits": bits, "M": a.M, "algo_bytes": ab, "nrot": nrot}
             for c in map(int, a.ctas.split(",")):
                 for pdl in (0, 1):
                     flags = _lib.APG_FLAG_PDL if pdl else 0
@@ -80,9 +81,9 @@ def main():
                     t = time_graph(fns)
                     rec[f"ours_c{c}_pdl{pdl}_us"] = round(t * 1e6, 3)
                     rec[f"ours_c{c}_pdl{pdl}_GBs"] = round(ab / t / 1e9, 1)
-            if refgpu.available() and not a.no_ref and N % 4 == 0:
+            if refgpu.available() and not a.no_ref and N % (4 if a.M == 1 else 16) == 0:
                 fns = [(lambda q=q: refgpu.ref().ref_anyprec_gemv(x.data_ptr(), out.data_ptr(), q.data_ptr(), lut.data_ptr(),
-                                                                   1, N, K, bits, torch.cuda.current_stream().cuda_stream)) for q in qs]
+                                                                   a.M, N, K, bits, torch.cuda.current_stream().cuda_stream)) for q in qs]
                 t = time_graph(fns)
                 rec["ref_us"] = round(t * 1e6, 3)
                 rec["ref_GBs"] = round(ab / t / 1e9, 1)
