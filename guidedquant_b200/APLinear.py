@@ -34,7 +34,14 @@ class APLinear(nn.Module):
         return self
 
     def gemm(self, x):
-        # prefill / seq > 1: dequant -> fp16 matmul (APLinear.py:35-38)
+        # prefill / seq > 1 (APLinear.py:35-38 does dequant -> fp16 matmul).  Up to 8 tokens go through the batched LUT
+        # GEMV instead (the kernel's M dimension, gemv.cu:41): the packed weights are read once and no fp16 copy of the
+        # matrix is written to HBM.  Longer sequences: dequant -> cuBLAS like the reference.
+        T = x.shape[1]
+        if T <= 8 and x.dtype == torch.float16 and x.is_cuda:
+            out = torch.empty((T, 1, self.out_features), dtype=torch.float16, device=x.device)
+            anyprec_gemv(x.reshape(T, 1, self.in_features).contiguous(), self.qweight, self.lut, out, self.bitwidth)
+            return out.reshape(1, T, self.out_features)
         weight = anyprec_dequant(self.qweight, self.lut, self.bitwidth)
         return torch.matmul(x, weight.T)
 

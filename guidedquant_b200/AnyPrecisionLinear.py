@@ -49,7 +49,13 @@ class AnyPrecisionLinear(nn.Module):
     def forward(self, x, **kwargs):
         w_bits = kwargs["precision"] if "precision" in kwargs else self.precision
         lut = self._buffers[f"lut{w_bits}"].to(torch.float16)
-        if x.numel() // x.shape[-1] > 1:
+        T = x.numel() // x.shape[-1]
+        if 1 < T <= 8 and x.is_cuda:
+            # short sequences: the batched LUT GEMV (kernel M dimension, gemv.cu:41) instead of dequant -> matmul
+            out = torch.empty((T, 1, self.out_features), dtype=torch.float16, device=x.device)
+            anyprec_gemv(x.to(torch.float16).reshape(T, 1, -1).contiguous(), self.qweight, lut, out, w_bits)
+            x = out.to(x.dtype).reshape(*x.shape[:-1], self.out_features)
+        elif T > 1:
             weight = ap_gemv.anyprec_dequant(self.qweight, lut, w_bits).to(x.dtype)
             x = torch.matmul(x, weight.T)
         else:

@@ -16,7 +16,7 @@ _CSRC = os.path.join(_PKG, "csrc")
 _LIBDIR = os.path.join(_PKG, "lib")
 LIB_PATH = os.path.join(_LIBDIR, "libapgemv_b200.so")
 _SOURCES = ["apgemv_capi.cu", "decode_capi.cu"]
-_HEADERS = ["apgemv_common.cuh", "apgemv_fast.cuh", "apgemv_generic.cuh", "decode_kernels.cuh"]
+_HEADERS = ["apgemv_common.cuh", "apgemv_fast.cuh", "apgemv_generic.cuh", "apgemv_wide.cuh", "decode_kernels.cuh"]
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-lineinfo", "-shared", "-Xcompiler", "-fPIC",

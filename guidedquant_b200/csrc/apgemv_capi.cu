@@ -9,6 +9,7 @@
 
 #include "apgemv_fast.cuh"
 #include "apgemv_generic.cuh"
+#include "apgemv_wide.cuh"
 
 namespace {
 
@@ -177,6 +178,49 @@ int launch_fast(const void *x, void *out, float *partial, const void *qweight, c
     return APG_ERR_UNSUPPORTED;
 }
 
+// every (bits, M) the fast kernel does not take: bits 5..8, M 2..8, K % 128 != 0, K > 32768 (apgemv_wide.cuh)
+template <int BITS, int R>
+int launch_wide_rows(const void *x, void *out, float *partial, const void *qweight, const void *lut, uint32_t M,
+                     uint32_t N, uint32_t K, cudaStream_t stream) {
+    const dim3 block(128), grid((N + 4 * R - 1) / (4 * R));  // 4 warps x R rows
+    const __half *xp = static_cast<const __half *>(x), *lp = static_cast<const __half *>(lut);
+    const uint32_t *wp = static_cast<const uint32_t *>(qweight);
+    __half *op = static_cast<__half *>(out);
+    if (M == 1) apg::gemv_wide_kernel<BITS, 1, R><<<grid, block, 0, stream>>>(xp, wp, lp, op, partial, M, N, K);
+    else if (M == 2) apg::gemv_wide_kernel<BITS, 2, R><<<grid, block, 0, stream>>>(xp, wp, lp, op, partial, M, N, K);
+    else if (M <= 4) apg::gemv_wide_kernel<BITS, 4, R><<<grid, block, 0, stream>>>(xp, wp, lp, op, partial, M, N, K);
+    else apg::gemv_wide_kernel<BITS, 8, R><<<grid, block, 0, stream>>>(xp, wp, lp, op, partial, M, N, K);
+    APG_CUDA(cudaGetLastError());
+    return APG_OK;
+}
+
+template <int BITS>
+int launch_wide_bits(const void *x, void *out, float *partial, const void *qweight, const void *lut, uint32_t M,
+                     uint32_t N, uint32_t K, cudaStream_t stream) {
+    // two rows per warp share every activation load; with few rows one row per warp keeps more warps in flight —
+    // except where the activation traffic dominates anyway (cheap pair-table dequant against 5..8 batch rows).
+    // Measured on B200, N = 4096, K = 4096 (us, R=1 / R=2): 2-bit M=2 5.3 / 6.9, 4-bit M=8 14.5 / 18.2, 8-bit M=1 9.6 / 11.5,
+    // 2-bit M=8 16.5 / 13.1.
+    static const uint32_t r1_max = getenv("APG_WIDE_R1_MAXN") ? (uint32_t)atoi(getenv("APG_WIDE_R1_MAXN")) : 8192u;
+    if (N <= r1_max && !(BITS <= 3 && M > 4))
+        return launch_wide_rows<BITS, 1>(x, out, partial, qweight, lut, M, N, K, stream);
+    return launch_wide_rows<BITS, 2>(x, out, partial, qweight, lut, M, N, K, stream);
+}
+
+int launch_wide(const void *x, void *out, float *partial, const void *qweight, const void *lut, uint32_t M, uint32_t N,
+                uint32_t K, int bits, cudaStream_t stream) {
+    switch (bits) {
+        case 2: return launch_wide_bits<2>(x, out, partial, qweight, lut, M, N, K, stream);
+        case 3: return launch_wide_bits<3>(x, out, partial, qweight, lut, M, N, K, stream);
+        case 4: return launch_wide_bits<4>(x, out, partial, qweight, lut, M, N, K, stream);
+        case 5: return launch_wide_bits<5>(x, out, partial, qweight, lut, M, N, K, stream);
+        case 6: return launch_wide_bits<6>(x, out, partial, qweight, lut, M, N, K, stream);
+        case 7: return launch_wide_bits<7>(x, out, partial, qweight, lut, M, N, K, stream);
+        case 8: return launch_wide_bits<8>(x, out, partial, qweight, lut, M, N, K, stream);
+        default: return APG_ERR_BITS;
+    }
+}
+
 }  // namespace
 
 extern "C" {
@@ -231,6 +275,8 @@ static int gemv_impl(const void *x, void *out, float *partial_f32, const void *q
         if (rc != APG_ERR_UNSUPPORTED) return rc;
     }
     if (fused) return APG_ERR_UNSUPPORTED;  // the fused prologue/epilogue exists in the fast kernel only
+    if (aligned(lut, 16) && !(flags & (APG_FLAG_REF_ORDER | APG_FLAG_GENERIC)))
+        return launch_wide(x, out, partial_f32, qweight, lut, M, N, K, bits, stream);
     const dim3 block(128), grid((N + 3) / 4);
     if (flags & APG_FLAG_REF_ORDER)
         gemv_generic_kernel<true><<<grid, block, 0, stream>>>(

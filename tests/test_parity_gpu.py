@@ -88,6 +88,26 @@ def test_ref_order_bit_exact_vs_oracle_and_generic(oracle, N, K, bits, M):
     assert _nerr(y0, y64) <= TOL_TRUTH
 
 
+@pytest.mark.parametrize("bits", [2, 3, 4, 5, 6, 7, 8])
+@pytest.mark.parametrize("N,K,M", [(33, 4096, 1), (7, 96, 2), (16, 1056, 3), (9, 11008, 4), (24, 2048, 5), (1, 1024, 8),
+                                   (40, 4128, 8), (8203, 1056, 3), (8200, 2048, 1)])  # N > 8192: two rows per warp
+def test_wide_gemv_vs_oracle(oracle, bits, N, K, M):
+    """the 'wide' kernel (bits 5..8, M 2..8, K % 128 != 0; apgemv_wide.cuh): default dispatch vs the fp64 truth, and
+    every batch row equal to the same row run alone (rows are independent)."""
+    idx, q, lut, x = oracle.synth_layer(N, K, bits, seed=17 * N + K + M + bits, M=M)
+    W = oracle.dequant(q, lut, bits)
+    y64 = oracle.gemv_f64(W, x)
+    xq, qq, ll = _t(x), _t(q), _t(lut)
+    y = _run(xq, qq, ll, bits)
+    yn = y.cpu().numpy().reshape(M, N)
+    assert not np.isnan(yn).any()
+    assert _nerr(yn, y64) <= TOL_TRUTH, (bits, N, K, M, _nerr(yn, y64))
+    if M > 1 and (bits > 4 or K % 128):  # single rows take the same kernel family: bit-identical
+        for m in (0, M - 1):
+            y1 = _run(xq[m:m + 1].contiguous(), qq, ll, bits)
+            assert torch.equal(y1.view(torch.int16).reshape(-1), y[m].view(torch.int16).reshape(-1)), (bits, m)
+
+
 @pytest.mark.parametrize("N,K,bits", [(64, 4096, 2), (64, 4096, 3), (64, 4096, 4), (16, 11008, 2), (16, 13824, 3),
                                        (8, 96, 4), (12, 1024, 5), (8, 2048, 8), (7, 1056, 2)])
 def test_dequant_bit_exact(oracle, N, K, bits):
@@ -207,8 +227,10 @@ def test_any_precision_linear_module(oracle):
         W = lut[np.arange(N)[:, None], idx]
         y64 = oracle.gemv_f64(W, x.cpu().numpy())
         assert _nerr(y, y64) <= TOL_TRUTH, bits
-        yp = m(x.expand(1, 3, K).contiguous())  # seq > 1 -> dequant + matmul
-        assert _nerr(yp[:, 0].float().cpu().numpy(), y64) <= 2e-3
+        yp = m(x.expand(1, 3, K).contiguous())  # 1 < seq <= 8 -> batched LUT GEMV
+        assert yp.shape == (1, 3, N) and _nerr(yp[:, 2].float().cpu().numpy(), y64) <= 2e-3
+        yl = m(x.expand(1, 11, K).contiguous())  # seq > 8 -> dequant + matmul (the reference's gemm path)
+        assert yl.shape == (1, 11, N) and _nerr(yl[:, 10].float().cpu().numpy(), y64) <= 2e-3
     with pytest.raises(RuntimeError):
         m.set_precision(2)
 
@@ -229,8 +251,10 @@ def test_aplinear_module_and_custom_op(oracle):
     y2 = torch.zeros_like(lin.output)
     torch.ops.plugin.anyprec_gemv(xq, lin.qweight, lin.lut, y2, bits)
     assert torch.equal(y2, lin.output)
-    yp = lin(xq.expand(1, 4, K).contiguous())
+    yp = lin(xq.expand(1, 4, K).contiguous())   # 1 < seq <= 8 -> batched LUT GEMV
     assert yp.shape == (1, 4, N) and _nerr(yp[:, 1].float().cpu().numpy(), y64) <= 2e-3
+    yl = lin(xq.expand(1, 12, K).contiguous())  # seq > 8 -> dequant + matmul (APLinear.py:35-38)
+    assert yl.shape == (1, 12, N) and _nerr(yl[:, 11].float().cpu().numpy(), y64) <= 2e-3
     # CUDA-graph capture of the op (how generate.py runs it)
     g = torch.cuda.CUDAGraph()
     s = torch.cuda.Stream()
