@@ -354,6 +354,23 @@ int apg_dequant(const void *qweight, const void *lut, void *w_out, uint32_t N, u
     if (bits < 2 || bits > 8) return APG_ERR_BITS;
     if (N < 1 || K < 32 || (K % 32u) != 0) return APG_ERR_SHAPE;
     if (!aligned(qweight, 4) || !aligned(lut, 2) || !aligned(w_out, 16)) return APG_ERR_ALIGN;
+    if (aligned(lut, 16)) {
+        const dim3 grid((N + 3) / 4), block(128);
+        const uint32_t *wp = static_cast<const uint32_t *>(qweight);
+        const __half *lp = static_cast<const __half *>(lut);
+        __half *op = static_cast<__half *>(w_out);
+        switch (bits) {
+            case 2: dequant_wide_kernel<2><<<grid, block, 0, stream>>>(wp, lp, op, N, K); break;
+            case 3: dequant_wide_kernel<3><<<grid, block, 0, stream>>>(wp, lp, op, N, K); break;
+            case 4: dequant_wide_kernel<4><<<grid, block, 0, stream>>>(wp, lp, op, N, K); break;
+            case 5: dequant_wide_kernel<5><<<grid, block, 0, stream>>>(wp, lp, op, N, K); break;
+            case 6: dequant_wide_kernel<6><<<grid, block, 0, stream>>>(wp, lp, op, N, K); break;
+            case 7: dequant_wide_kernel<7><<<grid, block, 0, stream>>>(wp, lp, op, N, K); break;
+            default: dequant_wide_kernel<8><<<grid, block, 0, stream>>>(wp, lp, op, N, K); break;
+        }
+        APG_CUDA(cudaGetLastError());
+        return APG_OK;
+    }
     dequant_kernel<<<dim3((N + 3) / 4), dim3(128), 0, stream>>>(static_cast<const uint32_t *>(qweight),
                                                                static_cast<const __half *>(lut),
                                                                static_cast<__half *>(w_out), N, K, bits);

@@ -221,4 +221,59 @@ __global__ void __launch_bounds__(128) gemv_wide_kernel(const __half *__restrict
         }
 }
 
+// W[n, k] = lut[n, idx[n, k]] (replaces dequant_kbit_store, anyprec.cu:294-359) on the wide kernel's machinery: one warp
+// per row, shared-memory codebook table, butterfly / pair-table index extraction; the 16 half2 registers of a chunk
+// are exactly four contiguous 16-byte pieces of the output row (k0(c) = i*1024 + c*8*eff + 8t), so every warp store is
+// a fully coalesced 512 B.  A pure gather of the codebook's bit patterns: bit-identical to the reference by construction.
+template <int BITS>
+__global__ void __launch_bounds__(128) dequant_wide_kernel(const uint32_t *__restrict__ W, const __half *__restrict__ lut,
+                                                           __half *__restrict__ O, uint32_t N, uint32_t K) {
+    constexpr int RTB = WideCfg<BITS>::ROW_TBL_BYTES;
+    constexpr int WTB = (RTB + 255) / 256 * 256;
+    __shared__ __align__(1024) uint8_t tb[4 * WTB];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t row = blockIdx.x * 4u + warp;
+    if (row >= N) return;
+    const uint32_t tbl = smem_u32(tb) + warp * WTB;
+    if constexpr (BITS <= 3) {
+        typename Tables<BITS, 1>::Regs lr;
+        Tables<BITS, 1>::fetch(lr, lut, row, N, lane);
+        Tables<BITS, 1>::store(lr, tbl, lane);
+    } else {
+        const uint4 *src = reinterpret_cast<const uint4 *>(lut + ((size_t)row << BITS));
+        for (int e = lane; e < (2 << BITS) / 16; e += 32) {
+            const uint4 v = __ldg(src + e);
+            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(tbl + e * 16), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+                         : "memory");
+        }
+    }
+    __syncwarp();
+    const uint32_t words = K >> 5, nchunk = (K + 1023u) >> 10;
+    uint32_t cur[BITS], nxt[BITS];
+    auto load_planes = [&](uint32_t i, uint32_t (&dst)[BITS]) {
+        if ((uint32_t)lane < chunk_eff(K, i)) {
+#pragma unroll
+            for (int j = 0; j < BITS; j++) dst[j] = ldg_stream_b32(W + ((size_t)j * N + row) * words + i * 32u + lane);
+        }
+    };
+    load_planes(0, cur);
+    for (uint32_t i = 0; i < nchunk; i++) {
+        if (i + 1 < nchunk) load_planes(i + 1, nxt);
+        const uint32_t eff = chunk_eff(K, i);
+        if ((uint32_t)lane < eff) {
+            uint32_t dq[16];
+            WideDequant<BITS, 0>::run(cur, tbl, dq);
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                __half *dst = O + (size_t)row * K + i * 1024u + c * 8u * eff + 8u * lane;
+                asm volatile("st.global.cs.v4.b32 [%0], {%1,%2,%3,%4};" ::"l"(dst), "r"(dq[4 * c + 0]), "r"(dq[4 * c + 1]),
+                             "r"(dq[4 * c + 2]), "r"(dq[4 * c + 3])
+                             : "memory");
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < BITS; j++) cur[j] = nxt[j];
+    }
+}
+
 }  // namespace apg

@@ -109,7 +109,8 @@ def test_wide_gemv_vs_oracle(oracle, bits, N, K, M):
 
 
 @pytest.mark.parametrize("N,K,bits", [(64, 4096, 2), (64, 4096, 3), (64, 4096, 4), (16, 11008, 2), (16, 13824, 3),
-                                       (8, 96, 4), (12, 1024, 5), (8, 2048, 8), (7, 1056, 2)])
+                                       (8, 96, 4), (12, 1024, 5), (8, 2048, 8), (7, 1056, 2), (9, 1120, 6), (5, 3072, 7),
+                                       (3, 11008, 4), (6, 2080, 3)])
 def test_dequant_bit_exact(oracle, N, K, bits):
     from guidedquant_b200 import ap_gemv
 
