@@ -60,7 +60,7 @@ inline bool aligned(const void *p, uintptr_t a) { return (reinterpret_cast<uintp
 constexpr size_t kFastMaxSmem = 200 * 1024;
 
 struct FastPlan {
-    uint32_t cpw, nwk, groups, rs, nslots, stage_bytes, grid, rows_per_cta, threads, tot_stages;
+    uint32_t cpw, nwk, groups, rs, nslots, stage_bytes, grid, rows_per_cta, threads, unit_rows, tot_units;
     size_t smem;
 };
 
@@ -91,9 +91,13 @@ bool plan_fast(uint32_t N, uint32_t K, int ctas_per_sm, int sms, FastPlan *pl) {
     if (grid > max_grid) grid = max_grid;
     if (grid < 1) grid = 1;
     pl->grid = grid;
-    const uint32_t tot_stages = (N + rs - 1) / rs;
-    pl->tot_stages = tot_stages;
-    const uint32_t stages_per_cta = (tot_stages + grid - 1) / grid;
+    // rows are dealt in half stages: with whole stages an SM ends up with e.g. 4 stages against an average of 3.46
+    // (N = 4096, RS = 8, 296 CTAs); a trailing half stage runs the half-length row loop
+    static const uint32_t half_stage = getenv("APG_HALF_STAGE") ? (uint32_t)atoi(getenv("APG_HALF_STAGE")) : 1u;
+    pl->unit_rows = half_stage ? rs / 2u : rs;
+    pl->tot_units = (N + pl->unit_rows - 1) / pl->unit_rows;
+    const uint32_t units_per_cta = (pl->tot_units + grid - 1) / grid;
+    const uint32_t stages_per_cta = (units_per_cta * pl->unit_rows + rs - 1) / rs;
     pl->rows_per_cta = stages_per_cta * rs;
     // ring: as deep as the CTA's share needs, bounded so that c CTAs (+ a dependent kernel's) fit in 227 KB
     const size_t ring_budget = (c >= 2 ? 56u : 96u) * 1024u;
@@ -152,8 +156,9 @@ int launch_fast(const void *x, void *out, float *partial, const void *qweight, c
     p.groups = pl.groups;
     p.nslots = pl.nslots;
     p.stage_bytes = pl.stage_bytes;
-    p.stages_q = pl.tot_stages / pl.grid;
-    p.stages_rem = pl.tot_stages % pl.grid;
+    p.unit_rows = pl.unit_rows;
+    p.units_q = pl.tot_units / pl.grid;
+    p.units_rem = pl.tot_units % pl.grid;
     p.inv_nwk = (65536u + pl.nwk - 1) / pl.nwk;
     p.norm_w = static_cast<const __half *>(fu.norm_w);
     p.norm_eps = fu.eps;

@@ -357,7 +357,8 @@ struct WordDot<4, ROW_OFF> {
 // that the table offset becomes an LDS immediate).  All RS rows are always computed (no per-row branch,
 // so the compiler can interleave rows); rows past the end of a partial stage read stale-but-mapped ring
 // bytes and are discarded by the caller.
-template <int BITS, int RS, int R>
+// REND = RS for a full stage, RS/2 for a stage that holds at most half the rows (the CTA's last one).
+template <int BITS, int RS, int R, int REND>
 struct RowLoop {
     __device__ __forceinline__ static void run(float (&acc)[RS], uint32_t pbase, uint32_t row_bytes, uint32_t plane_bytes,
                                                const uint32_t *xr, uint32_t tbl) {
@@ -365,11 +366,11 @@ struct RowLoop {
 #pragma unroll
         for (int j = 0; j < BITS; j++) pw[j] = lds_b32(pbase + j * plane_bytes);
         acc[R] = WordDot<BITS, R * FastCfg<BITS>::ROW_TBL_BYTES>::run(acc[R], pw, xr, tbl);
-        RowLoop<BITS, RS, R + 1>::run(acc, pbase + row_bytes, row_bytes, plane_bytes, xr, tbl);
+        RowLoop<BITS, RS, R + 1, REND>::run(acc, pbase + row_bytes, row_bytes, plane_bytes, xr, tbl);
     }
 };
-template <int BITS, int RS>
-struct RowLoop<BITS, RS, RS> {
+template <int BITS, int RS, int REND>
+struct RowLoop<BITS, RS, REND, REND> {
     __device__ __forceinline__ static void run(float (&)[RS], uint32_t, uint32_t, uint32_t, const uint32_t *, uint32_t) {}
 };
 
@@ -387,7 +388,8 @@ struct FastParams {
     uint32_t groups;         // row groups per CTA; consumer warps = groups * nwk; +1 producer warp
     uint32_t nslots;         // ring slots (multiple of groups)
     uint32_t stage_bytes;    // RS * BITS * K/8
-    uint32_t stages_q, stages_rem;  // stages per CTA: CTA b owns stages_q + (b < stages_rem) consecutive stages
+    uint32_t unit_rows;      // rows are dealt to CTAs in units of RS or RS/2 rows (half stages: finer balance over the SMs)
+    uint32_t units_q, units_rem;  // CTA b owns units_q + (b < units_rem) consecutive units
     uint32_t inv_nwk;        // ceil(65536 / nwk): warp / nwk == (warp * inv_nwk) >> 16 for warp < 64
     // ---- optional fusions of the ops that surround the Linear in the decode step (inference/model.py) ----
     const __half *norm_w;    // != nullptr: x := RMSNorm(x) * norm_w before the GEMV (model.py:280-285), eps below
@@ -425,13 +427,14 @@ __global__ void __launch_bounds__(544, 1) gemv_fast_kernel(const FastParams p) {
     const uint32_t ring0 = tbl0 + ncons * WTB;
     float *red = reinterpret_cast<float *>(smem_raw + (ring0 - smem0) + NS * p.stage_bytes);
 
-    // rows of this CTA: whole stages of RS rows (only the matrix's last stage can be partial)
-    const uint32_t s_begin = blockIdx.x * p.stages_q + min(blockIdx.x, p.stages_rem);
-    const uint32_t nstages = p.stages_q + (blockIdx.x < p.stages_rem ? 1u : 0u);
-    const uint32_t s_end = s_begin + nstages;
-    const uint32_t r_begin = s_begin * RS;
-    const uint32_t r_end = min(s_end * RS, N);
+    // rows of this CTA: consecutive units of unit_rows rows, walked in stages of RS rows; only the CTA's last stage can
+    // be partial, and a stage holding at most RS/2 rows is computed with the half-length row loop
+    const uint32_t u_begin = blockIdx.x * p.units_q + min(blockIdx.x, p.units_rem);
+    const uint32_t nunits = p.units_q + (blockIdx.x < p.units_rem ? 1u : 0u);
+    const uint32_t r_begin = min(u_begin * p.unit_rows, N);
+    const uint32_t r_end = min((u_begin + nunits) * p.unit_rows, N);
     const uint32_t nrows = r_end - r_begin;
+    const uint32_t nstages = (nrows + RS - 1) / RS;
 
     __half res_pref = __ushort_as_half(0);  // residual of row r_begin + threadIdx.x, prefetched by consumer threads
     if (threadIdx.x == 0) {
@@ -593,9 +596,16 @@ __global__ void __launch_bounds__(544, 1) gemv_fast_kernel(const FastParams p) {
             float acc[RS];
 #pragma unroll
             for (int r = 0; r < RS; r++) acc[r] = 0.f;
+            if (RS >= 2 && rows <= (uint32_t)(RS / 2)) {
 #pragma unroll
-            for (int cc = 0; cc < CPW; cc++)
-                if (act[cc]) RowLoop<BITS, RS, 0>::run(acc, stage + woff[cc], row_bytes, RS * row_bytes, xr[cc], tbl);
+                for (int cc = 0; cc < CPW; cc++)
+                    if (act[cc])
+                        RowLoop<BITS, RS, 0, (RS >= 2 ? RS / 2 : RS)>::run(acc, stage + woff[cc], row_bytes, RS * row_bytes, xr[cc], tbl);
+            } else {
+#pragma unroll
+                for (int cc = 0; cc < CPW; cc++)
+                    if (act[cc]) RowLoop<BITS, RS, 0, RS>::run(acc, stage + woff[cc], row_bytes, RS * row_bytes, xr[cc], tbl);
+            }
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_empty + 8u * slot);
 
