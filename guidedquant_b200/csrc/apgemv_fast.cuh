@@ -641,11 +641,4 @@ __global__ void __launch_bounds__(544, 1) gemv_fast_kernel(const FastParams p) {
     }
 }
 
-template <int BITS, int RS>
-inline size_t fast_smem_bytes(uint32_t ncons, uint32_t nslots, uint32_t stage_bytes, uint32_t rows_per_cta,
-                              uint32_t nwk) {
-    return 2 * (size_t)nslots * 8 + 512 + (size_t)ncons * FastWarpTbl<BITS, RS>::BYTES + (size_t)nslots * stage_bytes +
-           (size_t)rows_per_cta * nwk * sizeof(float) + 16;
-}
-
 }  // namespace apg
