@@ -111,9 +111,11 @@ class ClockSampler(threading.Thread):
                 "samples": len(s)}
 
 
-def cpu_reference_arm(model: str, bits: int, steps: int, warmup: int):
+def cpu_reference_arm(model: str, bits: int, steps: int, warmup: int, lm_head: bool = True):
     """The reference's CPU-runnable arm: dequant -> fp16 torch.matmul (APLinear.gemm, APLinear.py:35-38) of the
-    4 Linears of ONE block per step (a bounded 1/L sample of a token), all host cores."""
+    4 Linears of ONE block per step (a bounded 1/L sample of a token), all host cores; with `lm_head` the fp16 output
+    projection (model.py:94,129) is timed once and added per token.  Attention / norms / sampling at batch 1 are < 1 % of
+    the CPU token and are left out (which only flatters the CPU arm)."""
     import numpy as np
     import torch
 
@@ -146,8 +148,16 @@ def cpu_reference_arm(model: str, bits: int, steps: int, warmup: int):
     for _ in range(steps):
         block()
     t_block = (time.perf_counter() - t0) / steps
-    tok_s = 1.0 / (t_block * cfg["n_layer"])
-    return tok_s, t_block, cores, steps
+    t_head = 0.0
+    if lm_head:
+        Wh = torch.empty((cfg["vocab"], cfg["dim"]), dtype=torch.float16).normal_(0, 0.02)
+        xh = torch.randn((1, cfg["dim"])).half()
+        torch.matmul(xh, Wh.T)
+        t1 = time.perf_counter()
+        torch.matmul(xh, Wh.T)
+        t_head = time.perf_counter() - t1
+    tok_s = 1.0 / (t_block * cfg["n_layer"] + t_head)
+    return tok_s, t_block, cores, steps, t_head
 
 
 def main():
@@ -164,8 +174,12 @@ def main():
     if a.impl == "reference":
         if rank != 0:
             return
-        tok_s, t_block, cores, steps = cpu_reference_arm(model, a.bits, a.steps, a.warmup)
-        sample = f"1 block (wqkv, wo, w1w3, w2) of {model} per step, dequant->fp16 torch.matmul on CPU, value scaled by n_layer"
+        whole = a.workload == "decode"
+        tok_s, t_block, cores, steps, t_head = cpu_reference_arm(model, a.bits, a.steps, a.warmup, lm_head=whole)
+        if whole:  # same workload as our arm's default
+            workload = f"{model} {a.bits}-bit bs=1 decode, full token step: embed + L x (wqkv|attn|wo|w1w3|w2) + lm_head + greedy sample"
+        sample = (f"1 block (wqkv, wo, w1w3, w2) of {model} per step, dequant->fp16 torch.matmul on CPU, value = 1 / (n_layer x block"
+                  + (f" + fp16 lm_head {t_head:.2f} s)" if whole else ")"))
         line = {
             "impl": "reference", "metric": METRIC, "value": tok_s, "unit": UNIT, "n_gpus": max(world, a.gpus), "steps": steps, "warmup": 1,
             "ms_per_step": t_block * 1e3, "higher_is_better": True, "scaling": "strong" if max(world, a.gpus) > 1 else "weak",
@@ -326,9 +340,10 @@ def main():
     # CPU baseline (rank 0, N = 1 only): bounded sample
     if world == 1:
         try:
-            v, t_block, cores, st = cpu_reference_arm(model, a.bits, 2, 1)
+            v, t_block, cores, st, t_head = cpu_reference_arm(model, a.bits, 2, 1, lm_head=full_decode)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": f"{st} x 1 block (4 Linears) of {model}, dequant->fp16 torch.matmul, scaled by n_layer; {t_block:.2f} s/block"}
+                                    "sample": f"{st} x 1 block (4 Linears) of {model}, dequant->fp16 torch.matmul, scaled by n_layer; {t_block:.2f} s/block"
+                                              + (f" + fp16 lm_head {t_head:.2f} s/token" if full_decode else "")}
         except Exception as e:  # the GPU number must not be lost to a host-side failure
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e}"}
     print(json.dumps(line), flush=True)
