@@ -86,3 +86,49 @@ def test_worddot4_mapping(oracle, seed):
             c = 3 - b
             assert int(byte(ylo, b)) // 2 == truth[8 * c + 7 - sft]   # e_lo = 7 - sft
             assert int(byte(yhi, b)) // 2 == truth[8 * c + 3 - sft]   # e_hi = 3 - sft
+
+
+@pytest.mark.parametrize("bits", [4, 5, 6, 7, 8])
+@pytest.mark.parametrize("seed", range(3))
+def test_wide_butterfly_mapping(oracle, bits, seed):
+    """apgemv_wide.cuh WideDequant<4..8>: 8x8 bit-matrix butterfly transpose of the plane words; byte b of A[s] must be
+    (index << SH) of the weight at bit position 8b + s, i.e. k offset o = 8(3 - b) + (7 - s)."""
+    rng = np.random.default_rng(100 * bits + seed)
+    pw = [U(rng.integers(0, 2**32)) for _ in range(bits)]
+    truth = lane_indices(oracle, pw)
+    SH = 1 if bits <= 7 else 0
+    A = [U(0)] * 8
+    for r in range(8):
+        if r >= SH and r - SH < bits:
+            A[r] = pw[bits - 1 - (r - SH)]
+    for r in range(4):
+        a, b = A[r], A[r + 4]
+        A[r], A[r + 4] = bitsel(b << U(4), a, 0xF0F0F0F0), bitsel(b, a >> U(4), 0xF0F0F0F0)
+    for r in (0, 1, 4, 5):
+        a, b = A[r], A[r + 2]
+        A[r], A[r + 2] = bitsel(b << U(2), a, 0xCCCCCCCC), bitsel(b, a >> U(2), 0xCCCCCCCC)
+    for r in (0, 2, 4, 6):
+        a, b = A[r], A[r + 1]
+        A[r], A[r + 1] = bitsel(b << U(1), a, 0xAAAAAAAA), bitsel(b, a >> U(1), 0xAAAAAAAA)
+    for s in range(8):
+        for b in range(4):
+            v = int(byte(A[s], b))
+            assert v % (1 << SH) == 0 and (v >> SH) < (1 << bits)
+            assert (v >> SH) == truth[8 * (3 - b) + (7 - s)], (bits, s, b)
+
+
+def test_sampling_key_order_is_monotone():
+    """decode_kernels.cuh f16_order_key: ascending with the fp16 value, NaN lowest, -0 == +0, and invertible."""
+    h = np.arange(65536, dtype=np.uint32)
+    v = h.astype(np.uint16).view(np.float16).astype(np.float64)
+    nan = (h & 0x7FFF) > 0x7C00
+    hh = np.where(h == 0x8000, 0, h)
+    key = np.where(nan, 0, np.where(hh & 0x8000, ~hh & 0xFFFF, hh | 0x8000))
+    ok = ~nan
+    order = np.argsort(v[ok], kind="stable")
+    ks = key[ok][order]
+    assert np.all(np.diff(ks) >= 0)
+    assert np.all((np.diff(v[ok][order]) > 0) == (np.diff(ks) > 0))     # equal values <-> equal keys (only +-0)
+    back = np.where(key & 0x8000, key & 0x7FFF, ~key & 0xFFFF).astype(np.uint16).view(np.float16).astype(np.float64)
+    assert np.array_equal(back[ok], np.where(v[ok] == 0, 0.0, v[ok]))
+    assert key[ok].min() > 0
