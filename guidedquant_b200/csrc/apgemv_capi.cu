@@ -340,6 +340,21 @@ int apg_allreduce_finish(const void *recv, uint32_t *epoch, const void *residual
     return APG_OK;
 }
 
+int apg_plan_fast(uint32_t N, uint32_t K, int bits, int ctas_per_sm, int sms, uint32_t plan[16]) {
+    if (!plan) return APG_ERR_NULL;
+    if (bits < 2 || bits > 4) return APG_ERR_UNSUPPORTED;
+    if (N < 1 || K < 128 || (K % 128u) != 0 || K > 32768u || sms < 1) return APG_ERR_UNSUPPORTED;
+    FastPlan pl;
+    const bool ok = bits == 2 ? plan_fast<2>(N, K, ctas_per_sm, sms, &pl)
+                              : (bits == 3 ? plan_fast<3>(N, K, ctas_per_sm, sms, &pl) : plan_fast<4>(N, K, ctas_per_sm, sms, &pl));
+    if (!ok) return APG_ERR_UNSUPPORTED;
+    const uint32_t v[16] = {pl.cpw, pl.nwk, pl.groups, pl.rs, pl.nslots, pl.stage_bytes, pl.grid, pl.rows_per_cta,
+                            pl.threads, pl.unit_rows, pl.tot_units / pl.grid, pl.tot_units % pl.grid, (uint32_t)pl.smem,
+                            0u, 0u, 0u};
+    for (int i = 0; i < 16; i++) plan[i] = v[i];
+    return APG_OK;
+}
+
 int apg_prefetch_hint(const void *next_weights, uint64_t bytes) {
     g_prefetch_ptr = next_weights;
     g_prefetch_bytes = next_weights ? bytes : 0;

@@ -116,6 +116,17 @@ int apg_allreduce_finish(const void *recv, uint32_t *epoch, const void *residual
 int apg_prefetch_hint(const void *next_weights, uint64_t bytes);
 
 /*
+ * Introspection of the fast kernel's work decomposition (host only, no GPU needed): how apg_gemv would cut an
+ * N x K, `bits`-bit Linear on a device with `sms` SMs.  Returns APG_ERR_UNSUPPORTED when the fast kernel does not take
+ * the shape.  plan[0..15] = { chunks_per_warp, chunk_warps_per_group, groups, rows_per_stage, ring_slots, stage_bytes,
+ * grid, red_rows_per_cta, threads, unit_rows, units_q, units_rem, smem_bytes, 0, 0, 0 }: CTA b owns the rows
+ * [u*unit_rows, (u + n)*unit_rows) with u = b*units_q + min(b, units_rem), n = units_q + (b < units_rem), walked in
+ * stages of rows_per_stage rows dealt round-robin to the groups.  Used by the CPU tests to check that every row is
+ * covered exactly once and that the shared-memory budget holds for every shape.
+ */
+int apg_plan_fast(uint32_t N, uint32_t K, int bits, int ctas_per_sm, int sms, uint32_t plan[16]);
+
+/*
  * Replaces ap_gemv.anyprec_dequant(qweight, lut, bitwidth) -> fp16 [N, K]
  *   (inference/ap_gemv/gemv.cu:109-134 -> dequant_kbit_store, anyprec.cu:294-359, 622-645).
  * w_out[n, k] = lut[n, idx[n, k]] — a pure gather, bit-identical to the reference.

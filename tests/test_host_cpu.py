@@ -132,3 +132,54 @@ def test_checkpoint_converter_matches_reference_converter():
     # layer count comes from the keys (the reference only accepts Llama-2 directory names)
     small = {k: v for k, v in make_hf_checkpoint(n_layer=3).items()}
     assert "layers.2.attention.wqkv.qweight" in convert_state_dict(small, 2)
+
+
+def test_fast_kernel_work_decomposition_covers_every_row_once():
+    """apg_plan_fast exposes the host-side plan of the fast GEMV kernel; replay the kernel's own row arithmetic
+    (apgemv_fast.cuh: units -> rows -> stages -> groups/slots) for many shapes and check the invariants the device code
+    relies on: rows partitioned exactly, only a CTA's last stage partial, ring slots a multiple of the groups, the
+    reduction buffer large enough, shared memory within the opt-in budget, block size within the launch bound."""
+    import ctypes
+
+    from guidedquant_b200 import _lib
+
+    L = _lib.lib()
+    plan = (ctypes.c_uint32 * 16)()
+    shapes = [(N, K) for N in (1, 3, 4, 7, 8, 9, 100, 1184, 1185, 4096, 6144, 8192, 10240, 14336, 28672, 57344, 128256)
+              for K in (128, 1024, 1152, 2048, 3584, 4096, 7168, 8192, 11008, 14336, 28672, 32768)]
+    checked = 0
+    for N, K in shapes:
+        for bits in (2, 3, 4):
+            for ctas in (0, 1, 2, 3):
+                for sms in (148, 132, 8):
+                    rc = L.apg_plan_fast(N, K, bits, ctas, sms, ctypes.byref(plan))
+                    if rc != 0:
+                        assert rc == 8, rc  # APG_ERR_UNSUPPORTED: falls to the wide kernel
+                        continue
+                    cpw, nwk, G, RS, NS, stage_bytes, grid, red_rows, threads, unit, uq, urem, smem = list(plan)[:13]
+                    nchunk = (K + 1023) // 1024
+                    assert cpw in (1, 2) and nwk == (nchunk + cpw - 1) // cpw and 1 <= nwk <= 16
+                    assert threads == (G * nwk + 1) * 32 <= 544
+                    assert RS in (2, 4, 8) and unit in (RS, RS // 2) and unit >= 1
+                    assert stage_bytes == RS * bits * K // 8
+                    assert NS >= G and NS % G == 0
+                    assert smem <= 200 * 1024
+                    assert 1 <= grid <= max(1, sms * (ctas if ctas > 0 else 2))
+                    # replay the kernel's partition
+                    nxt, max_rows = 0, 0
+                    for b in range(grid):
+                        u0 = b * uq + min(b, urem)
+                        n = uq + (1 if b < urem else 0)
+                        r0, r1 = min(u0 * unit, N), min((u0 + n) * unit, N)
+                        assert r0 == nxt, (N, K, bits, b)
+                        nxt = r1
+                        nrows = r1 - r0
+                        max_rows = max(max_rows, nrows)
+                        nstages = (nrows + RS - 1) // RS
+                        for s in range(nstages):
+                            rows = min(RS, r1 - (r0 + s * RS))
+                            assert rows >= 1 and (rows == RS or s == nstages - 1)
+                    assert nxt == N, (N, K, bits, ctas, sms)
+                    assert max_rows <= red_rows
+                    checked += 1
+    assert checked > 2000
