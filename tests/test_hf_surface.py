@@ -97,3 +97,42 @@ def test_logits_match_dense_model_gpu(ckpt):
         del ref
     out = m.generate(ids[:, :2], max_new_tokens=4, do_sample=False, precision=3)
     assert out.shape == (1, 6) and m.precision == 4
+
+
+def test_checkpoint_container_variants_cpu(ckpt, tmp_path):
+    """the loader accepts what HF tooling may have re-saved the packer's output as: safetensors, and sharded files with
+    an index json (any_precision checkpoints on the hub ship pytorch_model.bin; pack.py:199)."""
+    import json
+
+    from safetensors.torch import save_file
+
+    from guidedquant_b200.AnyPrecisionForCausalLM import AnyPrecisionForCausalLM
+
+    d, cfg, _ = ckpt
+    sd = torch.load(os.path.join(d, "pytorch_model.bin"), weights_only=True)
+    ref = AnyPrecisionForCausalLM.from_quantized(d, device="cpu").model.state_dict()
+
+    st = tmp_path / "st"
+    st.mkdir()
+    save_file({k: v.contiguous() for k, v in sd.items()}, str(st / "model.safetensors"))
+    cfg.save_pretrained(str(st))
+    got = AnyPrecisionForCausalLM.from_quantized(str(st), device="cpu").model.state_dict()
+    assert got.keys() == ref.keys() and all(torch.equal(got[k], ref[k]) for k in ref)
+
+    sh = tmp_path / "sharded"
+    sh.mkdir()
+    keys = sorted(sd)
+    parts = {"pytorch_model-00001-of-00002.bin": keys[: len(keys) // 2], "pytorch_model-00002-of-00002.bin": keys[len(keys) // 2:]}
+    for fn, ks in parts.items():
+        torch.save({k: sd[k] for k in ks}, sh / fn)
+    json.dump({"metadata": {}, "weight_map": {k: fn for fn, ks in parts.items() for k in ks}},
+              open(sh / "pytorch_model.bin.index.json", "w"))
+    cfg.save_pretrained(str(sh))
+    got = AnyPrecisionForCausalLM.from_quantized(str(sh), device="cpu").model.state_dict()
+    assert got.keys() == ref.keys() and all(torch.equal(got[k], ref[k]) for k in ref)
+
+    empty = tmp_path / "empty"
+    empty.mkdir()
+    cfg.save_pretrained(str(empty))
+    with pytest.raises(FileNotFoundError, match="no checkpoint file"):
+        AnyPrecisionForCausalLM.from_quantized(str(empty), device="cpu")
