@@ -20,13 +20,13 @@ What is different, and why:
 from __future__ import annotations
 
 import gc
-import json
 import os
 
 import torch
 import torch.nn as nn
 
 from .AnyPrecisionLinear import AnyPrecisionLinear
+from .convert import read_checkpoint
 
 
 def _resolve(root, dotted: str):
@@ -39,30 +39,6 @@ def _resolve(root, dotted: str):
 def _swap(root, dotted: str, new: nn.Module) -> None:
     head, _, leaf = dotted.rpartition(".")
     setattr(_resolve(root, head) if head else root, leaf, new)
-
-
-def _read_checkpoint(model_path: str) -> dict:
-    """pytorch_model.bin (what the reference packer writes), or safetensors / sharded variants of either."""
-    cands = ["pytorch_model.bin", "model.safetensors", "pytorch_model.bin.index.json", "model.safetensors.index.json"]
-    for name in cands:
-        p = os.path.join(model_path, name)
-        if not os.path.exists(p):
-            continue
-        if name.endswith(".index.json"):
-            files = sorted(set(json.load(open(p))["weight_map"].values()))
-        else:
-            files = [name]
-        sd = {}
-        for f in files:
-            fp = os.path.join(model_path, f)
-            if f.endswith(".safetensors"):
-                from safetensors.torch import load_file
-
-                sd.update(load_file(fp))
-            else:
-                sd.update(torch.load(fp, map_location="cpu", mmap=True, weights_only=True))
-        return sd
-    raise FileNotFoundError(f"no checkpoint file ({', '.join(cands)}) under {model_path}")
 
 
 class AnyPrecisionForCausalLM(nn.Module):
@@ -117,7 +93,7 @@ class AnyPrecisionForCausalLM(nn.Module):
                 _swap(layer, name, q)
 
     def _materialize(self, model_path, device, dtype):
-        sd = _read_checkpoint(model_path)
+        sd = read_checkpoint(model_path)
         # modules that own non-persistent buffers (rotary inv_freq) cannot be restored from a state dict: rebuild them
         rebuilt = []
         for name, m in list(self.model.named_modules()):

@@ -58,8 +58,49 @@ def convert_state_dict(ckpt: dict, bitwidth: int) -> dict:
     return new
 
 
+def read_checkpoint(model_path: str) -> dict:
+    """pytorch_model.bin (what the reference packer writes, pack.py:199), or safetensors / sharded variants of either."""
+    import json
+
+    cands = ["pytorch_model.bin", "model.safetensors", "pytorch_model.bin.index.json", "model.safetensors.index.json"]
+    for name in cands:
+        p = os.path.join(model_path, name)
+        if not os.path.exists(p):
+            continue
+        files = sorted(set(json.load(open(p))["weight_map"].values())) if name.endswith(".index.json") else [name]
+        sd = {}
+        for f in files:
+            fp = os.path.join(model_path, f)
+            if f.endswith(".safetensors"):
+                from safetensors.torch import load_file
+
+                sd.update(load_file(fp))
+            else:
+                sd.update(torch.load(fp, map_location="cpu", mmap=True, weights_only=True))
+        return sd
+    raise FileNotFoundError(f"no checkpoint file ({', '.join(cands)}) under {model_path}")
+
+
+def arch_from_hf_config(hf: dict) -> tuple[dict, float, float]:
+    """(model config, rope base, rms-norm eps) of a Llama-family config.json; refuses what the decode kernels do not
+    implement (head_dim != 128, scaled RoPE variants) instead of producing silently wrong logits."""
+    n_head = hf["num_attention_heads"]
+    head_dim = hf.get("head_dim") or hf["hidden_size"] // n_head
+    if head_dim != 128:
+        raise NotImplementedError(f"head_dim {head_dim}: the attention kernel is specialised for 128")
+    rp = hf.get("rope_parameters") or {}                      # transformers >= 5 nests the RoPE settings
+    scaling = hf.get("rope_scaling") or ({k: v for k, v in rp.items() if k != "rope_theta"} if rp else None)
+    kind = (scaling or {}).get("rope_type", (scaling or {}).get("type", "default"))
+    if kind not in (None, "default"):
+        raise NotImplementedError(f"rope scaling '{kind}' is not implemented (default RoPE only, model.py:353)")
+    theta = hf.get("rope_theta", rp.get("rope_theta", 10000.0))
+    cfg = dict(dim=hf["hidden_size"], n_layer=hf["num_hidden_layers"], n_head=n_head,
+               n_kv=hf.get("num_key_value_heads") or n_head, inter=hf["intermediate_size"], vocab=hf["vocab_size"])
+    return cfg, float(theta), float(hf.get("rms_norm_eps", 1e-5))
+
+
 def convert_checkpoint(ckpt_dir: str, bitwidth: int, out_name: str = "converted_pytorch_model.bin") -> str:
-    ckpt = torch.load(os.path.join(ckpt_dir, "pytorch_model.bin"), map_location="cpu", weights_only=True)
+    ckpt = read_checkpoint(ckpt_dir)
     out = os.path.join(ckpt_dir, out_name)
     torch.save(convert_state_dict(ckpt, bitwidth), out)
     return out

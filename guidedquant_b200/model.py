@@ -161,21 +161,17 @@ class APTransformer:
         import json
         import os
 
-        from .convert import convert_state_dict
+        from .convert import arch_from_hf_config, convert_state_dict, read_checkpoint
 
         hf = json.load(open(os.path.join(ckpt_dir, "config.json")))
         name = "ckpt:" + os.path.basename(os.path.normpath(ckpt_dir))
-        MODEL_CONFIGS[name] = dict(dim=hf["hidden_size"], n_layer=hf["num_hidden_layers"], n_head=hf["num_attention_heads"],
-                                   n_kv=hf.get("num_key_value_heads", hf["num_attention_heads"]),
-                                   inter=hf["intermediate_size"], vocab=hf["vocab_size"])
-        ROPE_BASE[name] = float(hf.get("rope_theta", 10000.0))
-        m = cls(name, bits=bitwidth, max_seq_len=max_seq_len, norm_eps=float(hf.get("rms_norm_eps", 1e-5)), **kw)
+        MODEL_CONFIGS[name], ROPE_BASE[name], eps = arch_from_hf_config(hf)
+        m = cls(name, bits=bitwidth, max_seq_len=max_seq_len, norm_eps=eps, **kw)
         conv = os.path.join(ckpt_dir, "converted_pytorch_model.bin")
         if os.path.exists(conv):
             sd = torch.load(conv, map_location="cpu", mmap=True, weights_only=True)
         else:
-            sd = convert_state_dict(torch.load(os.path.join(ckpt_dir, "pytorch_model.bin"), map_location="cpu",
-                                               weights_only=True), bitwidth)
+            sd = convert_state_dict(read_checkpoint(ckpt_dir), bitwidth)
         sd = {k: (v.half() if v.is_floating_point() else v) for k, v in sd.items()}
         return m.load_state_dict(sd)
 

@@ -183,3 +183,42 @@ def test_fast_kernel_work_decomposition_covers_every_row_once():
                     assert max_rows <= red_rows
                     checked += 1
     assert checked > 2000
+
+
+def test_arch_from_hf_config_and_checkpoint_reader(tmp_path):
+    """the CPU half of APTransformer.from_checkpoint: config.json -> (arch, rope base, eps) for both spellings of the RoPE
+    settings, loud refusal of what the kernels do not implement, and the checkpoint reader on a .bin directory."""
+    import torch
+
+    from guidedquant_b200.convert import arch_from_hf_config, convert_state_dict, read_checkpoint
+
+    base = {"hidden_size": 256, "num_hidden_layers": 2, "num_attention_heads": 2, "num_key_value_heads": 1,
+            "intermediate_size": 512, "vocab_size": 128, "rms_norm_eps": 1e-5}
+    cfg, theta, eps = arch_from_hf_config({**base, "rope_theta": 500000.0})           # transformers 4.x (the reference pins 4.52)
+    assert cfg == dict(dim=256, n_layer=2, n_head=2, n_kv=1, inter=512, vocab=128) and theta == 500000.0 and eps == 1e-5
+    cfg2, theta2, _ = arch_from_hf_config({**base, "rope_parameters": {"rope_theta": 10000.0, "rope_type": "default"}})  # 5.x
+    assert cfg2 == cfg and theta2 == 10000.0
+    assert arch_from_hf_config({**base, "rope_scaling": None})[1] == 10000.0          # default base
+    mha = dict(base)
+    del mha["num_key_value_heads"]
+    assert arch_from_hf_config(mha)[0]["n_kv"] == 2                                    # MHA checkpoints omit the key
+    with pytest.raises(NotImplementedError, match="rope scaling"):
+        arch_from_hf_config({**base, "rope_scaling": {"rope_type": "llama3", "factor": 8.0}})
+    with pytest.raises(NotImplementedError, match="rope scaling"):
+        arch_from_hf_config({**base, "rope_parameters": {"rope_theta": 5e5, "rope_type": "yarn", "factor": 4.0}})
+    with pytest.raises(NotImplementedError, match="head_dim"):
+        arch_from_hf_config({**base, "num_attention_heads": 4})
+
+    sd = {"model.embed_tokens.weight": torch.zeros((4, 8), dtype=torch.bfloat16)}
+    for pj, n in (("q", 8), ("k", 4), ("v", 4)):
+        sd[f"model.layers.0.self_attn.{pj}_proj.qweight"] = torch.zeros((4, n, 1), dtype=torch.int32)
+        sd[f"model.layers.0.self_attn.{pj}_proj.lut3"] = torch.zeros((n, 8), dtype=torch.float16)
+        sd[f"model.layers.0.self_attn.{pj}_proj.lut4"] = torch.zeros((n, 16), dtype=torch.float16)
+    torch.save(sd, tmp_path / "pytorch_model.bin")
+    got = read_checkpoint(str(tmp_path))
+    assert got.keys() == sd.keys() and all(torch.equal(got[k], sd[k]) for k in sd)
+    conv = convert_state_dict(got, 3)
+    assert conv["layers.0.attention.wqkv.qweight"].shape == (3, 16, 1) and conv["layers.0.attention.wqkv.lut"].shape == (16, 8)
+    assert conv["tok_embeddings.weight"].dtype == torch.float16
+    with pytest.raises(FileNotFoundError):
+        read_checkpoint(str(tmp_path / "nothing-here"))
