@@ -112,13 +112,13 @@ bool plan_fast(uint32_t N, uint32_t K, int ctas_per_sm, int sms, FastPlan *pl) {
     return pl->smem <= kFastMaxSmem;
 }
 
-template <int BITS, int CPW, int RS>
+template <int BITS, int CPW, int RS, bool GLU = false>
 int launch_fast_inst(const apg::FastParams &p, const FastPlan &pl, uint32_t flags, cudaStream_t stream) {
     static bool attr_set[64] = {false};
     int dev = 0;
     APG_CUDA(cudaGetDevice(&dev));
     if (!attr_set[dev & 63]) {
-        APG_CUDA(cudaFuncSetAttribute(apg::gemv_fast_kernel<BITS, CPW, RS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        APG_CUDA(cudaFuncSetAttribute(apg::gemv_fast_kernel<BITS, CPW, RS, GLU>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)kFastMaxSmem));
         attr_set[dev & 63] = true;
     }
@@ -134,7 +134,7 @@ int launch_fast_inst(const apg::FastParams &p, const FastPlan &pl, uint32_t flag
         cfg.attrs = attr;
         cfg.numAttrs = 1;
     }
-    APG_CUDA(cudaLaunchKernelEx(&cfg, apg::gemv_fast_kernel<BITS, CPW, RS>, p));
+    APG_CUDA(cudaLaunchKernelEx(&cfg, apg::gemv_fast_kernel<BITS, CPW, RS, GLU>, p));
     return APG_OK;
 }
 
@@ -162,7 +162,11 @@ int launch_fast(const void *x, void *out, float *partial, const void *qweight, c
     p.inv_nwk = (65536u + pl.nwk - 1) / pl.nwk;
     p.norm_w = static_cast<const __half *>(fu.norm_w);
     p.norm_eps = fu.eps;
-    p.act_silu_mul = fu.silu_mul ? 1u : 0u;
+    p.act_silu_mul = fu.silu_mul == 1 ? 1u : 0u;
+    if (fu.silu_mul == 2) {  // experimental GLU epilogue: interleaved (gate, up) rows, out has N / 2 elements
+        if ((N & 1u) || (pl.unit_rows & 1u) || pl.cpw != 1 || pl.rs != 8 || !out || partial || fu.residual || fu.world > 1)
+            return APG_ERR_UNSUPPORTED;
+    }
     p.residual = static_cast<const __half *>(fu.residual);
     p.world = fu.world;
     p.rank = fu.rank;
@@ -171,6 +175,7 @@ int launch_fast(const void *x, void *out, float *partial, const void *qweight, c
     p.epoch = static_cast<const uint32_t *>(fu.epoch);
     p.prefetch = static_cast<const uint8_t *>(prefetch);
     p.prefetch_bytes = (prefetch && aligned(prefetch, 16)) ? prefetch_bytes : 0;
+    if (fu.silu_mul == 2) return launch_fast_inst<BITS, 1, 8, true>(p, pl, flags, stream);
 #define APG_FAST_CASE(CPW_, RS_) \
     if (pl.cpw == CPW_ && pl.rs == RS_) return launch_fast_inst<BITS, CPW_, RS_>(p, pl, flags, stream);
     APG_FAST_CASE(1, 8)

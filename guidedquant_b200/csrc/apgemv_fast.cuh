@@ -408,7 +408,10 @@ struct FastParams {
 };
 
 // smem: [barriers 2*nslots*8 | pad->256 | tables (per consumer warp) | ring nslots*stage_bytes | red floats]
-template <int BITS, int CPW, int RS>
+// GLU = true (experimental, selected by apg_gemv_fused(silu_mul = 2)): the Linear's rows are interleaved (gate_i, up_i)
+// and the epilogue writes out[i] = silu(y[2i]) * y[2i+1] — the FeedForward activation (model.py:261-266) computed once
+// per element here instead of by every CTA of the w2 launch that follows.  The default instantiations are unchanged.
+template <int BITS, int CPW, int RS, bool GLU = false>
 __global__ void __launch_bounds__(544, 1) gemv_fast_kernel(const FastParams p) {
     constexpr int WTB = FastWarpTbl<BITS, RS>::BYTES;
     using Tb = Tables<BITS, RS>;
@@ -619,6 +622,18 @@ __global__ void __launch_bounds__(544, 1) gemv_fast_kernel(const FastParams p) {
     }
 
     __syncthreads();
+    if constexpr (GLU) {
+        // r_begin and nrows are even (units of RS/2 = 4 rows, N even): thread t combines the row pair (2t, 2t+1) with the
+        // same roundings as the w2 prologue it replaces (y -> fp16, silu in fp32 -> fp16, fp16 product)
+        for (uint32_t r = 2u * threadIdx.x; r + 1u < nrows; r += 2u * blockDim.x) {
+            float vg = red[r * nwk], vu = red[(r + 1u) * nwk];
+            for (uint32_t w = 1; w < nwk; w++) vg += red[r * nwk + w], vu += red[(r + 1u) * nwk + w];
+            const float gf = __half2float(__float2half_rn(vg));
+            const __half sg = __float2half_rn(__fdividef(gf, 1.f + __expf(-gf)));
+            p.out[(r_begin + r) >> 1] = __hmul(sg, __float2half_rn(vu));
+        }
+        return;
+    }
     const uint32_t ep = (p.world > 1) ? (*p.epoch + 1u) : 0u;
     // fixed-order combination of the per-chunk partial sums -> deterministic results
     for (uint32_t r = threadIdx.x; r < nrows; r += blockDim.x) {

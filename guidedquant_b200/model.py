@@ -34,13 +34,18 @@ MODEL_CONFIGS.setdefault("tiny128kv4", dict(dim=1024, n_layer=2, n_head=8, n_kv=
 class APTransformer:
     def __init__(self, model: str = "llama3-8b", bits: int = 2, max_seq_len: int = 256, device=None, pdl: bool = True,
                  norm_eps: float = 1e-5, n_layer: int | None = None, attn_splits: int | None = None,
-                 world_size: int = 1, rank: int = 0, process_group=None):
+                 world_size: int = 1, rank: int = 0, process_group=None, glu_epilogue: bool = False):
         self.cfg = dict(MODEL_CONFIGS[model])
         if n_layer is not None:
             self.cfg["n_layer"] = n_layer
         c = self.cfg
         assert c["dim"] // c["n_head"] == 128, "the attention kernel is specialised for head_dim 128"
         self.model, self.bits, self.S, self.eps = model, bits, max_seq_len, norm_eps
+        # EXPERIMENTAL (off by default, not yet measured on a GPU): keep w1w3's rows interleaved (gate_i, up_i) so that its
+        # epilogue writes silu(gate)*up once per element (apg_gemv_fused(silu_mul=2)) instead of every CTA of the w2 launch
+        # recomputing the activation in its prologue.  Same roundings -> same logits.  Single GPU only.
+        self.glu_epilogue = bool(glu_epilogue)
+        assert not (self.glu_epilogue and world_size > 1), "glu_epilogue is single-GPU only"
         self.flags = _lib.APG_FLAG_PDL if pdl else 0
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
         self.rope_base = ROPE_BASE.get(model, 10000.0)
@@ -111,7 +116,7 @@ class APTransformer:
             sd[f"layers.{i}.post_attention_layernorm.weight"] = (1 + 0.1 * torch.randn(c["dim"], device=dev, generator=g)).half()
         sd["norm.weight"] = (1 + 0.1 * torch.randn(c["dim"], device=dev, generator=g)).half()
         sd["output.weight"] = (torch.randn((c["vocab"], c["dim"]), device=dev, generator=g) / math.sqrt(c["dim"])).half()
-        if self.world > 1:  # every rank generated the same full model; keep this rank's shards
+        if self.world > 1 or self.glu_epilogue:  # shard / re-order through the common path
             self.sd = {}
             self.load_state_dict(sd)
         return self
@@ -119,7 +124,12 @@ class APTransformer:
     def load_state_dict(self, sd: dict):
         """full (unsharded) state dict in; with world_size > 1 the Linears are sharded for this rank on the way."""
         for k, v in sd.items():
-            self.sd[k] = self._shard(k, v.to(self.device)).contiguous()
+            t = self._shard(k, v.to(self.device))
+            if self.glu_epilogue and ".w1w3." in k:  # rows (gate | up) -> (gate_0, up_0, gate_1, up_1, ...)
+                inter = self.cfg["inter"]
+                idx = torch.stack([torch.arange(inter), inter + torch.arange(inter)], dim=1).reshape(-1).to(t.device)
+                t = t.index_select(1 if k.endswith(".qweight") else 0, idx)
+            self.sd[k] = t.contiguous()
         return self
 
     def _shard(self, name: str, t: torch.Tensor) -> torch.Tensor:
@@ -224,8 +234,10 @@ class APTransformer:
               self.launches_per_token += 1 + (1 if self.nsplit > 1 else 0)
             if self.push is None:
                 self._fused(self.att, self.h, p + "attention.wo", no, ko, residual=self.x)
-                self._fused(self.h, self.gu, p + "feed_forward.w1w3", ng, kg, norm=sd[p + "post_attention_layernorm.weight"])
-                self._fused(self.gu, self.x, p + "feed_forward.w2", n2, k2, silu_mul=1, residual=self.h)
+                glu = self.glu_epilogue
+                self._fused(self.h, self.gu, p + "feed_forward.w1w3", ng, kg, norm=sd[p + "post_attention_layernorm.weight"],
+                            silu_mul=2 if glu else 0)
+                self._fused(self.gu, self.x, p + "feed_forward.w2", n2, k2, silu_mul=0 if glu else 1, residual=self.h)
             else:  # K-sharded wo / w2: partial sums pushed to every peer from the GEMV epilogue, residual added by the finisher
                 self.push.gemv_push(2 * i, self.att, sd[p + "attention.wo.qweight"], sd[p + "attention.wo.lut"], no, ko,
                                     self.bits, flags=fl)

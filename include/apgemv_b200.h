@@ -79,7 +79,11 @@ int apg_gemv_ex(const void *x, void *out, float *partial_f32, const void *qweigh
  * M = 1 GEMV fused with the element-wise ops that surround a Linear in the reference's decode step
  * (inference/model.py), so that a transformer block is 5 launches instead of 11:
  *   norm_w   != NULL: x := (fp16)(x * rsqrt(mean(x^2) + norm_eps)) * norm_w       RMSNorm.forward, model.py:280-285
- *   silu_mul != 0   : x := silu(x[0:K]) * x[K:2K]  (x holds 2K halfs)             FeedForward.forward, model.py:261-266
+ *   silu_mul == 1   : x := silu(x[0:K]) * x[K:2K]  (x holds 2K halfs)             FeedForward.forward, model.py:261-266
+ *   silu_mul == 2   : EXPERIMENTAL (built, not yet measured): the rows of THIS Linear are interleaved (gate_0, up_0, gate_1,
+ *                     ...) and out[N/2] receives silu(y[2i]) * y[2i+1] with the roundings of the silu_mul == 1 prologue it
+ *                     replaces; needs N even, K <= 8192 (one chunk per warp), no residual / partial / multi-GPU push,
+ *                     else APG_ERR_UNSUPPORTED
  *   residual != NULL: out := (fp16)y + residual  (fp16 add)                       TransformerBlock.forward, model.py:151-167
  * Fast-path shapes only (bits 2..4, K % 128 == 0, K <= 32768); otherwise APG_ERR_UNSUPPORTED.
  */

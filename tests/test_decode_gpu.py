@@ -3,6 +3,8 @@ against oracle/decode_oracle.py — itself pinned to the reference's inference/m
 Tolerance: logits within 2e-2 of max|logits| (fp16 activations through L blocks; the GEMV accumulates fp16 chains ->
 fp32 while the oracle rounds once per Linear), and identical greedy tokens wherever the oracle's top-2 margin exceeds
 that tolerance."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -238,3 +240,15 @@ def test_generate_with_temperature():
     assert a == b and len(a) == 21 and all(0 <= t < cfg["vocab"] for t in a)
     assert a != c                              # the seed matters: noise is actually applied
     assert m.generate([1], 20, temperature=0.0) == greedy
+
+
+@pytest.mark.skipif(not os.environ.get("APG_TEST_EXPERIMENTAL"), reason="experimental GLU epilogue: opt in with APG_TEST_EXPERIMENTAL=1")
+@pytest.mark.parametrize("bits", [2, 3, 4])
+def test_experimental_glu_epilogue_equals_default(bits):
+    """apg_gemv_fused(silu_mul=2): silu(gate)*up in the w1w3 epilogue on interleaved rows == the default w2 prologue."""
+    from guidedquant_b200.model import APTransformer
+
+    a = APTransformer("tiny128", bits=bits, max_seq_len=32).random_init(5)
+    b = APTransformer("tiny128", bits=bits, max_seq_len=32, glu_epilogue=True).random_init(5)
+    assert a.generate([1, 7, 3], 12) == b.generate([1, 7, 3], 12)
+    assert torch.equal(a.logits, b.logits)
