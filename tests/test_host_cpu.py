@@ -222,3 +222,24 @@ def test_arch_from_hf_config_and_checkpoint_reader(tmp_path):
     assert conv["tok_embeddings.weight"].dtype == torch.float16
     with pytest.raises(FileNotFoundError):
         read_checkpoint(str(tmp_path / "nothing-here"))
+
+
+def test_roofline_arithmetic_matches_the_survey_table():
+    """the algorithmic-byte figures bench.py's roofline uses == SURVEY.md §8 (shape table and §8d)."""
+    from guidedquant_b200.runtime import MODEL_CONFIGS, gemv_algo_bytes, linear_shapes
+
+    assert gemv_algo_bytes(4096, 4096, 2) == 4_194_304 + 32_768 + 8_192 + 8_192 == 4_243_456          # §8d worked example
+    s8 = linear_shapes(MODEL_CONFIGS["llama3-8b"])
+    assert s8 == {"wqkv": (6144, 4096), "wo": (4096, 4096), "w1w3": (28672, 4096), "w2": (4096, 14336)}
+    s70 = linear_shapes(MODEL_CONFIGS["llama3-70b"])
+    assert s70 == {"wqkv": (10240, 8192), "wo": (8192, 8192), "w1w3": (57344, 8192), "w2": (8192, 28672)}
+    assert linear_shapes(MODEL_CONFIGS["llama2-70b"]) == s70
+    per_block = sum(N * K for N, K in s8.values())
+    assert per_block == 218_103_808                                                                  # weights per block
+    for bits, gb in ((2, 1.745), (3, 2.617), (4, 3.490)):                                             # planes per token
+        assert abs(32 * per_block * bits / 8 / 1e9 - gb) < 1e-3
+    rows = sum(N for N, _ in s8.values()) * 32
+    assert rows == 1_376_256 and rows * 4 * 2 == 11_010_048                                           # 2-bit LUT bytes/token
+    assert 2 * MODEL_CONFIGS["llama3-8b"]["vocab"] * 4096 == 1_050_673_152                           # fp16 lm_head
+    planes = {n: 2 * N * K // 8 for n, (N, K) in s8.items()}
+    assert planes == {"wqkv": 6_291_456, "wo": 4_194_304, "w1w3": 29_360_128, "w2": 14_680_064}
