@@ -31,28 +31,60 @@ EXPORTS = (
 )
 
 
+def _source_hash() -> str:
+    import hashlib
+
+    h = hashlib.sha256()
+    h.update(" ".join(NVCC_FLAGS).encode())
+    for d in [os.path.join(_CSRC, f) for f in sorted(_SOURCES + _HEADERS)] + [os.path.join(_ROOT, "include", "apgemv_b200.h"),
+                                                                            os.path.join(_ROOT, "include", "apdecode_b200.h")]:
+        if os.path.exists(d):
+            h.update(os.path.basename(d).encode())
+            h.update(open(d, "rb").read())
+    return h.hexdigest()
+
+
+_HASH_PATH = LIB_PATH + ".srchash"
+
+
 def _stale() -> bool:
-    if not os.path.exists(LIB_PATH):
+    """the library is stale when it was built from other sources than the ones in the tree (content hash, not mtimes:
+    a snapshot copy of the tree does not preserve them)"""
+    if not os.path.exists(LIB_PATH) or not os.path.exists(_HASH_PATH):
         return True
-    t = os.path.getmtime(LIB_PATH)
-    deps = [os.path.join(_CSRC, f) for f in _SOURCES + _HEADERS] + [os.path.join(_ROOT, "include", "apgemv_b200.h")]
-    return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
+    return open(_HASH_PATH).read().strip() != _source_hash()
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    """nvcc -gencode arch=compute_100a,code=sm_100a ... -> guidedquant_b200/lib/libapgemv_b200.so"""
+    """nvcc -gencode arch=compute_100a,code=sm_100a ... -> guidedquant_b200/lib/libapgemv_b200.so
+    Built into a temporary file and renamed into place under a file lock, so concurrent ranks (torchrun on a fresh tree)
+    neither write the same output nor load a partially written library."""
+    import fcntl
+
     if not force and not _stale():
         return LIB_PATH
     os.makedirs(_LIBDIR, exist_ok=True)
-    srcs = [os.path.join(_CSRC, f) for f in _SOURCES if os.path.exists(os.path.join(_CSRC, f))]
-    cmd = ["nvcc", *NVCC_FLAGS, "-I" + os.path.join(_ROOT, "include"), "-I" + _CSRC, "-o", LIB_PATH, *srcs]
-    if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        raise RuntimeError("nvcc failed building libapgemv_b200.so:\n" + res.stdout + res.stderr)
-    if verbose:
-        print(res.stderr)
+    with open(os.path.join(_LIBDIR, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not _stale():  # another process built it while we waited
+                return LIB_PATH
+            srcs = [os.path.join(_CSRC, f) for f in _SOURCES if os.path.exists(os.path.join(_CSRC, f))]
+            tmp = LIB_PATH + f".tmp{os.getpid()}"
+            cmd = ["nvcc", *NVCC_FLAGS, "-I" + os.path.join(_ROOT, "include"), "-I" + _CSRC, "-o", tmp, *srcs]
+            if verbose:
+                cmd.insert(1, "-Xptxas=-v")
+            res = subprocess.run(cmd, capture_output=True, text=True)
+            if res.returncode != 0:
+                raise RuntimeError("nvcc failed building libapgemv_b200.so:\n" + res.stdout + res.stderr)
+            if verbose:
+                print(res.stderr)
+            os.replace(tmp, LIB_PATH)
+            with open(_HASH_PATH + ".tmp", "w") as f:
+                f.write(_source_hash())
+            os.replace(_HASH_PATH + ".tmp", _HASH_PATH)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB_PATH
 
 
@@ -64,15 +96,17 @@ def lib() -> ctypes.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    if _stale():  # missing, or built from other sources than the tree holds (an ABI mismatch waiting to happen)
         try:
             build()
-        except Exception as e:  # no nvcc on this box and no prebuilt library
+        except Exception as e:  # no nvcc on this box and no matching prebuilt library
             raise RuntimeError(
-                f"libapgemv_b200.so is missing ({LIB_PATH}) and could not be built: {e}. "
+                f"libapgemv_b200.so is missing or stale ({LIB_PATH}) and could not be built: {e}. "
                 "Run `python -c 'import __graft_entry__ as g; g.build()'` where nvcc is available."
             ) from e
     L = ctypes.CDLL(LIB_PATH)
+    if L.apg_version() != APG_VERSION:
+        raise RuntimeError(f"libapgemv_b200.so reports version {L.apg_version()}, this package expects {APG_VERSION}")
     vp, u32, i32 = ctypes.c_void_p, ctypes.c_uint32, ctypes.c_int
     L.apg_version.restype = i32
     L.apg_status_string.restype = ctypes.c_char_p
@@ -122,6 +156,7 @@ def check(status: int, what: str) -> None:
         raise RuntimeError(f"{what}: {msg}{extra}")
 
 
+APG_VERSION = 200  # include/apgemv_b200.h: major*100 + minor
 APG_FLAG_REF_ORDER = 0x1
 APG_FLAG_GENERIC = 0x2
 APG_FLAG_PDL = 0x4

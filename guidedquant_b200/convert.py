@@ -81,9 +81,33 @@ def read_checkpoint(model_path: str) -> dict:
     raise FileNotFoundError(f"no checkpoint file ({', '.join(cands)}) under {model_path}")
 
 
+def rope_inv_freq(theta: float, scaling: dict | None = None, head_dim: int = 128) -> torch.Tensor:
+    """fp32 inv_freq[head_dim / 2] of the rotary embedding (inference/model.py:353 -> transformers' ROPE_INIT_FUNCTIONS):
+    "default" and the Llama-3.1 frequency rescaling ("llama3": low frequencies divided by `factor`, a smooth ramp between
+    the two wavelength thresholds; attention_scaling stays 1).  Host-side: it only changes the 64-entry table."""
+    import math
+
+    inv = 1.0 / (theta ** (torch.arange(0, head_dim, 2, dtype=torch.int64).float() / head_dim))
+    kind = (scaling or {}).get("rope_type", (scaling or {}).get("type", "default"))
+    if kind in (None, "default"):
+        return inv
+    if kind != "llama3":
+        raise NotImplementedError(f"rope scaling '{kind}' is not implemented (default and llama3 only)")
+    factor, lo, hi = scaling["factor"], scaling["low_freq_factor"], scaling["high_freq_factor"]
+    old_len = scaling["original_max_position_embeddings"]
+    low_wl, high_wl = old_len / lo, old_len / hi
+    wavelen = 2 * math.pi / inv
+    out = torch.where(wavelen > low_wl, inv / factor, inv)
+    smooth = (old_len / wavelen - lo) / (hi - lo)
+    smoothed = (1 - smooth) * out / factor + smooth * out
+    medium = ~(wavelen < high_wl) & ~(wavelen > low_wl)
+    return torch.where(medium, smoothed, out)
+
+
 def arch_from_hf_config(hf: dict) -> tuple[dict, float, float]:
     """(model config, rope base, rms-norm eps) of a Llama-family config.json; refuses what the decode kernels do not
-    implement (head_dim != 128, scaled RoPE variants) instead of producing silently wrong logits."""
+    implement (head_dim != 128, RoPE scalings other than llama3) instead of producing silently wrong logits.  A llama3
+    scaling dict is returned inside the model config under "rope_scaling"."""
     n_head = hf["num_attention_heads"]
     head_dim = hf.get("head_dim") or hf["hidden_size"] // n_head
     if head_dim != 128:
@@ -91,11 +115,13 @@ def arch_from_hf_config(hf: dict) -> tuple[dict, float, float]:
     rp = hf.get("rope_parameters") or {}                      # transformers >= 5 nests the RoPE settings
     scaling = hf.get("rope_scaling") or ({k: v for k, v in rp.items() if k != "rope_theta"} if rp else None)
     kind = (scaling or {}).get("rope_type", (scaling or {}).get("type", "default"))
-    if kind not in (None, "default"):
-        raise NotImplementedError(f"rope scaling '{kind}' is not implemented (default RoPE only, model.py:353)")
+    if kind not in (None, "default", "llama3"):
+        raise NotImplementedError(f"rope scaling '{kind}' is not implemented (default and llama3 only, model.py:337-353)")
     theta = hf.get("rope_theta", rp.get("rope_theta", 10000.0))
     cfg = dict(dim=hf["hidden_size"], n_layer=hf["num_hidden_layers"], n_head=n_head,
                n_kv=hf.get("num_key_value_heads") or n_head, inter=hf["intermediate_size"], vocab=hf["vocab_size"])
+    if kind == "llama3":
+        cfg["rope_scaling"] = dict(scaling)
     return cfg, float(theta), float(hf.get("rms_norm_eps", 1e-5))
 
 

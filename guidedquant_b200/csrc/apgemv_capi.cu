@@ -30,6 +30,10 @@ inline int cuda_fail(cudaError_t e) {
     g_last_cuda_error = (int)e;
     return APG_ERR_CUDA;
 }
+}  // namespace
+// shared with decode_capi.cu: every failing CUDA call of the library lands in apg_last_cuda_error()
+int apg_internal_cuda_fail(int e) { return cuda_fail((cudaError_t)e); }
+namespace {
 #define APG_CUDA(call)                                   \
     do {                                                 \
         cudaError_t e__ = (call);                        \

@@ -7,6 +7,8 @@
 #include "apgemv_b200.h"
 #include "decode_kernels.cuh"
 
+int apg_internal_cuda_fail(int e);  // apgemv_capi.cu: records the error for apg_last_cuda_error()
+
 namespace {
 template <typename... KArgs, typename... Args>
 int launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, uint32_t flags, void *stream, Args... args) {
@@ -22,7 +24,8 @@ int launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, uint32_t 
         cfg.attrs = attr;
         cfg.numAttrs = 1;
     }
-    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...) == cudaSuccess ? APG_OK : APG_ERR_CUDA;
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+    return e == cudaSuccess ? APG_OK : apg_internal_cuda_fail((int)e);
 }
 inline bool al(const void *p, uintptr_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
 }  // namespace
@@ -58,8 +61,9 @@ int apd_lm_head(const void *x, const void *norm_w, float eps, const void *W, voi
     if (V == 0 || D == 0 || D % 256 || D > 8192) return APG_ERR_SHAPE;
     if (!al(W, 16) || !al(x, 2) || !al(norm_w, 2)) return APG_ERR_ALIGN;
     int dev = 0, sms = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
-        return APG_ERR_CUDA;
+    cudaError_t ce = cudaGetDevice(&dev);
+    if (ce == cudaSuccess) ce = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (ce != cudaSuccess) return apg_internal_cuda_fail((int)ce);
     const uint32_t nv = D / 256;
     static const uint32_t per_sm = getenv("APD_LMHEAD_CTAS") ? (uint32_t)atoi(getenv("APD_LMHEAD_CTAS")) : 6u;  // measured on B200: 2 -> 5.1 TB/s, 4 -> 6.5, 6 -> 6.6
     uint32_t grid = (uint32_t)sms * per_sm;

@@ -34,8 +34,11 @@ MODEL_CONFIGS.setdefault("tiny128kv4", dict(dim=1024, n_layer=2, n_head=8, n_kv=
 class APTransformer:
     def __init__(self, model: str = "llama3-8b", bits: int = 2, max_seq_len: int = 256, device=None, pdl: bool = True,
                  norm_eps: float = 1e-5, n_layer: int | None = None, attn_splits: int | None = None,
-                 world_size: int = 1, rank: int = 0, process_group=None, glu_epilogue: bool = False):
+                 world_size: int = 1, rank: int = 0, process_group=None, glu_epilogue: bool = False,
+                 engine: str | None = None):
         self.cfg = dict(MODEL_CONFIGS[model])
+        self.engine = engine or "launches"
+        assert self.engine in ("launches",), f"unknown decode engine {engine!r}"
         if n_layer is not None:
             self.cfg["n_layer"] = n_layer
         c = self.cfg
@@ -82,7 +85,9 @@ class APTransformer:
         self.pos = torch.zeros(1, dtype=torch.int32, device=dev)
         self.history = torch.zeros(max_seq_len + 1, dtype=torch.int32, device=dev)
         hd = 128
-        self.inv_freq = (1.0 / (self.rope_base ** (torch.arange(0, hd, 2, dtype=torch.int64).float() / hd))).to(dev)
+        from .convert import rope_inv_freq
+
+        self.inv_freq = rope_inv_freq(self.rope_base, c.get("rope_scaling"), hd).to(dev)   # default or llama3-scaled table
         self.k_cache = [torch.zeros((self.Hkv_l, max_seq_len, hd), dtype=f16, device=dev) for _ in range(c["n_layer"])]
         self.v_cache = [torch.zeros((self.Hkv_l, max_seq_len, hd), dtype=f16, device=dev) for _ in range(c["n_layer"])]
         self.part = torch.zeros(self.H_l * self.nsplit * 132, dtype=torch.float32, device=dev) if self.nsplit > 1 else None
@@ -90,6 +95,7 @@ class APTransformer:
         self.stream = torch.cuda.Stream(device=dev)
         self.tok_host = torch.zeros(1, dtype=torch.int32).pin_memory()
         self.launches_per_token = 0
+        self._pos_host = 0   # host mirror of the device-side position (bound check in step / step_host)
         # measured on B200: launching the 1 GB lm_head stream programmatically (early, beside the last w2) costs
         # ~250 us/token; it is launched as a plain stream-ordered kernel instead
         self.lm_head_no_pdl = _lib.APG_FLAG_PDL
@@ -121,10 +127,48 @@ class APTransformer:
             self.load_state_dict(sd)
         return self
 
+    def expected_keys(self) -> list[str]:
+        c = self.cfg
+        keys = ["tok_embeddings.weight", "norm.weight", "output.weight"]
+        for i in range(c["n_layer"]):
+            keys += [f"layers.{i}.input_layernorm.weight", f"layers.{i}.post_attention_layernorm.weight"]
+            for mod, names in (("attention", ("wqkv", "wo")), ("feed_forward", ("w1w3", "w2"))):
+                for nm in names:
+                    keys += [f"layers.{i}.{mod}.{nm}.qweight", f"layers.{i}.{mod}.{nm}.lut"]
+        return keys
+
+    def _validate(self, name: str, t: torch.Tensor) -> torch.Tensor:
+        """shape / dtype check of one FULL (unsharded) tensor against (bits, N, K) — what load_state_dict(strict=True) of the
+        reference's nn.Module does (generate.py:239); a qweight with more planes than `bits` (any-precision parent) is
+        sliced to its first `bits` planes like sqllm_llama_convert_fuse.py:59-60."""
+        c = self.cfg
+        parts = name.split(".")
+        if name.endswith(".qweight") or name.endswith(".lut"):
+            N, K = self.shapes[parts[-2]]
+            if name.endswith(".qweight"):
+                if t.dtype != torch.int32 or t.dim() != 3 or t.shape[0] < self.bits or tuple(t.shape[1:]) != (N, K // 32):
+                    raise ValueError(f"{name}: expected int32 [>={self.bits}, {N}, {K // 32}], got {t.dtype} {tuple(t.shape)}")
+                return t[:self.bits]
+            if t.dtype != torch.float16 or tuple(t.shape) != (N, 1 << self.bits):
+                raise ValueError(f"{name}: expected float16 [{N}, {1 << self.bits}] (a {self.bits}-bit codebook), got {t.dtype} "
+                                 f"{tuple(t.shape)} — was the checkpoint converted for another bitwidth?")
+            return t
+        want = {"tok_embeddings.weight": (c["vocab"], c["dim"]), "output.weight": (c["vocab"], c["dim"])}.get(name, (c["dim"],))
+        if t.dtype != torch.float16 or tuple(t.shape) != want:
+            raise ValueError(f"{name}: expected float16 {want}, got {t.dtype} {tuple(t.shape)}")
+        return t
+
     def load_state_dict(self, sd: dict):
-        """full (unsharded) state dict in; with world_size > 1 the Linears are sharded for this rank on the way."""
-        for k, v in sd.items():
-            t = self._shard(k, v.to(self.device))
+        """full (unsharded) state dict in; with world_size > 1 the Linears are sharded for this rank on the way.  Strict:
+        every expected key must be present with the shape / dtype (bits, N, K) imply, unexpected keys are refused."""
+        exp = self.expected_keys()
+        missing = [k for k in exp if k not in sd]
+        unexpected = [k for k in sd if k not in set(exp)]
+        if missing or unexpected:
+            raise KeyError(f"state dict mismatch: missing {missing[:6]}{'...' if len(missing) > 6 else ''}, "
+                           f"unexpected {unexpected[:6]}{'...' if len(unexpected) > 6 else ''}")
+        for k in exp:
+            t = self._shard(k, self._validate(k, sd[k]).to(self.device))
             if self.glu_epilogue and ".w1w3." in k:  # rows (gate | up) -> (gate_0, up_0, gate_1, up_1, ...)
                 inter = self.cfg["inter"]
                 idx = torch.stack([torch.arange(inter), inter + torch.arange(inter)], dim=1).reshape(-1).to(t.device)
@@ -183,7 +227,10 @@ class APTransformer:
         else:
             sd = convert_state_dict(read_checkpoint(ckpt_dir), bitwidth)
         sd = {k: (v.half() if v.is_floating_point() else v) for k, v in sd.items()}
-        return m.load_state_dict(sd)
+        if "output.weight" not in sd and hf.get("tie_word_embeddings"):
+            sd["output.weight"] = sd["tok_embeddings.weight"]
+        sd = {k: v for k, v in sd.items() if not k.endswith("rotary_emb.inv_freq")}
+        return m.load_state_dict(sd)  # validates every tensor against (bitwidth, N, K): a file converted for another bitwidth is refused
 
     # ------------------------------------------------------------------ accounting
     def algo_bytes_per_token(self, pos: int = 0) -> dict:
@@ -303,6 +350,7 @@ class APTransformer:
         return self
 
     def reset(self, first_token: int = 1):
+        self._pos_host = 0
         with torch.cuda.stream(self.stream):
             self.token.fill_(first_token)
             self.pos.zero_()
@@ -310,9 +358,17 @@ class APTransformer:
             self.history[0] = first_token
         self.stream.synchronize()
 
+    def _advance_host_pos(self):
+        # the attention kernel refuses positions >= max_seq_len (it leaves `out` untouched) while the sampler would still
+        # advance: track the position on the host and raise instead of producing tokens from stale attention output
+        if self._pos_host >= self.S:
+            raise RuntimeError(f"KV cache full: position {self._pos_host} >= max_seq_len {self.S} (reset() or build with a larger max_seq_len)")
+        self._pos_host += 1
+
     def step(self):
         if self.graph is None:
             self.capture()
+        self._advance_host_pos()
         with torch.cuda.stream(self.stream):
             self.graph.replay()
 
@@ -320,6 +376,7 @@ class APTransformer:
         """end-to-end call for one token: pinned-host token id -> H2D -> graph -> D2H of the sampled token."""
         if self.graph is None:
             self.capture()
+        self._advance_host_pos()
         with torch.cuda.stream(self.stream):
             self.token.copy_(token_host, non_blocking=True)
             self.graph.replay()

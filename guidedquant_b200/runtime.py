@@ -62,8 +62,10 @@ class _Lin:
 class ApGemvChain:
     def __init__(self, model: str = "llama3-8b", bits: int = 2, device=None, seed: int = 0, n_layer: int | None = None,
                  pdl: bool = True, world_size: int = 1, rank: int = 0, process_group=None, ctas_per_sm: int = 0,
-                 l2_prefetch: bool = False, collective: str = "push"):
+                 l2_prefetch: bool = False, collective: str = "push", engine: str | None = None):
         self.cfg = dict(MODEL_CONFIGS[model])
+        self.engine = engine or "launches"
+        assert self.engine in ("launches",), f"unknown engine {engine!r}"
         if n_layer is not None:
             self.cfg["n_layer"] = n_layer
         self.model, self.bits, self.pdl = model, bits, pdl

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define APG_VERSION 100 /* major*100 + minor */
+#define APG_VERSION 200 /* major*100 + minor */
 
 enum apg_status {
     APG_OK = 0,

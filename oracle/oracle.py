@@ -149,11 +149,11 @@ def synth_layer(N: int, K: int, bits: int, seed: int = 0, M: int = 1, sorted_lut
 
 # ------------------------------------------------- CPU baseline of the reference path (timed leg)
 def cpu_reference_linear(qweight: np.ndarray, lut: np.ndarray, x: np.ndarray, bits: int, threads: int | None = None,
-                         dequant_each_call: bool = True, repeats: int = 1):
+                         dequant_each_call: bool = True, repeats: int = 1, matmul_dtype: str = "f16"):
     """The reference's own CPU-runnable arm (BASELINE.json configs[0]): dequant -> fp16 torch.matmul
     on the host cores, mirroring APLinear.gemm (APLinear.py:35-38: anyprec_dequant then
     torch.matmul(x, W.T)).  Returns (y float16 [M,N], seconds per call, threads used).
-    The gather is vectorised numpy over indices produced by the C oracle's unpack."""
+    The dequant is the C oracle's unpack + gather, row blocks dealt to `threads` host threads."""
     import torch
 
     threads = threads or os.cpu_count() or 1
@@ -161,19 +161,43 @@ def cpu_reference_linear(qweight: np.ndarray, lut: np.ndarray, x: np.ndarray, bi
     q = np.ascontiguousarray(qweight)
     K = q.shape[2] * 32
     xt = torch.from_numpy(np.ascontiguousarray(x).reshape(-1, K))
-    lut_t = torch.from_numpy(np.ascontiguousarray(lut))
+    lut = np.ascontiguousarray(lut)
 
     def deq():
-        idx = torch.from_numpy(unpack(q, bits).astype(np.int64))
-        return torch.gather(lut_t, 1, idx)
+        # the C oracle's dequant (unpack + gather) is single-threaded; deal row blocks to `threads` host threads (ctypes
+        # releases the GIL), which is what a threaded CPU implementation of anyprec_dequant would do
+        N = q.shape[1]
+        nblk = max(1, min(threads, N // 64))
+        bounds = [N * i // nblk for i in range(nblk + 1)]
+        out = np.empty((N, K), dtype=np.float16)
+
+        def one(i):
+            r0, r1 = bounds[i], bounds[i + 1]
+            out[r0:r1] = dequant(np.ascontiguousarray(q[:bits, r0:r1]), lut[r0:r1], bits)
+
+        if nblk == 1:
+            one(0)
+        else:
+            from concurrent.futures import ThreadPoolExecutor
+
+            with ThreadPoolExecutor(nblk) as ex:
+                list(ex.map(one, range(nblk)))
+        return torch.from_numpy(out)
 
     W = None if dequant_each_call else deq()
+    if matmul_dtype == "f32":  # resident fp32 copy of the dense weight ("fp16 and fp32")
+        xt = xt.float()
+        if W is not None:
+            W = W.float()
     t0 = time.perf_counter()
     for _ in range(repeats):
         Wc = deq() if dequant_each_call else W
+        if matmul_dtype == "f32" and dequant_each_call:
+            Wc = Wc.float()
         try:
             y = torch.matmul(xt, Wc.T)
         except RuntimeError:  # no fp16 CPU matmul in this torch build
             y = torch.matmul(xt.float(), Wc.float().T).half()
+    y = y.half()
     dt = (time.perf_counter() - t0) / repeats
     return y.numpy(), dt, threads

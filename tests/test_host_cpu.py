@@ -202,8 +202,10 @@ def test_arch_from_hf_config_and_checkpoint_reader(tmp_path):
     mha = dict(base)
     del mha["num_key_value_heads"]
     assert arch_from_hf_config(mha)[0]["n_kv"] == 2                                    # MHA checkpoints omit the key
-    with pytest.raises(NotImplementedError, match="rope scaling"):
-        arch_from_hf_config({**base, "rope_scaling": {"rope_type": "llama3", "factor": 8.0}})
+    l3 = {"rope_type": "llama3", "factor": 8.0, "low_freq_factor": 1.0, "high_freq_factor": 4.0,
+          "original_max_position_embeddings": 8192}
+    cfg3, theta3, _ = arch_from_hf_config({**base, "rope_theta": 500000.0, "rope_scaling": l3})   # Llama-3.1 (README.md:46-49)
+    assert cfg3["rope_scaling"]["factor"] == 8.0 and theta3 == 500000.0
     with pytest.raises(NotImplementedError, match="rope scaling"):
         arch_from_hf_config({**base, "rope_parameters": {"rope_theta": 5e5, "rope_type": "yarn", "factor": 4.0}})
     with pytest.raises(NotImplementedError, match="head_dim"):
@@ -243,3 +245,29 @@ def test_roofline_arithmetic_matches_the_survey_table():
     assert 2 * MODEL_CONFIGS["llama3-8b"]["vocab"] * 4096 == 1_050_673_152                           # fp16 lm_head
     planes = {n: 2 * N * K // 8 for n, (N, K) in s8.items()}
     assert planes == {"wqkv": 6_291_456, "wo": 4_194_304, "w1w3": 29_360_128, "w2": 14_680_064}
+
+
+def test_llama3_rope_table_matches_transformers():
+    """the llama3 frequency rescaling (what the reference gets from ROPE_INIT_FUNCTIONS["llama3"], inference/model.py:353)
+    against transformers' own init function, and the default table against the closed form."""
+    import torch
+    from guidedquant_b200.convert import rope_inv_freq
+
+    l3 = {"rope_type": "llama3", "factor": 8.0, "low_freq_factor": 1.0, "high_freq_factor": 4.0,
+          "original_max_position_embeddings": 8192}
+    ours = rope_inv_freq(500000.0, l3, 128)
+    base = 1.0 / (500000.0 ** (torch.arange(0, 128, 2, dtype=torch.int64).float() / 128))
+    assert torch.equal(rope_inv_freq(500000.0, None, 128), base)
+    assert torch.equal(ours[:20], base[:20]) and torch.allclose(ours[-1], base[-1] / 8.0)   # high freqs kept, low ones / factor
+    try:
+        from transformers import LlamaConfig
+        from transformers.modeling_rope_utils import ROPE_INIT_FUNCTIONS
+    except Exception:
+        pytest.skip("transformers rope utilities not importable")
+    try:
+        cfg = LlamaConfig(hidden_size=4096, num_attention_heads=32, rope_theta=500000.0, rope_scaling=dict(l3),
+                          max_position_embeddings=131072)
+        ref, scale = ROPE_INIT_FUNCTIONS["llama3"](cfg, "cpu")
+    except Exception as e:  # config spelling differs between transformers versions
+        pytest.skip(f"transformers llama3 rope init not callable here: {e}")
+    assert scale == 1.0 and torch.allclose(ours, ref.float(), rtol=1e-6, atol=0)
