@@ -15,11 +15,12 @@ _ROOT = os.path.dirname(_PKG)
 _CSRC = os.path.join(_PKG, "csrc")
 _LIBDIR = os.path.join(_PKG, "lib")
 LIB_PATH = os.path.join(_LIBDIR, "libapgemv_b200.so")
-_SOURCES = ["apgemv_capi.cu", "decode_capi.cu"]
-_HEADERS = ["apgemv_common.cuh", "apgemv_fast.cuh", "apgemv_generic.cuh", "apgemv_wide.cuh", "decode_kernels.cuh"]
+_SOURCES = ["apgemv_capi.cu", "decode_capi.cu", "persist_capi.cu"]
+_HEADERS = ["apgemv_common.cuh", "apgemv_fast.cuh", "apgemv_generic.cuh", "apgemv_wide.cuh", "decode_kernels.cuh",
+            "apgemv_persist.cuh"]
 
 NVCC_FLAGS = [
-    "-O3", "-std=c++17", "-lineinfo", "-shared", "-Xcompiler", "-fPIC",
+    "-O3", "-std=c++17", "-lineinfo", "-shared", "-Xcompiler", "-fPIC", "-t", "4",
     "-gencode", "arch=compute_100a,code=sm_100a",
 ]
 
@@ -28,6 +29,8 @@ EXPORTS = (
     "apg_round_f32_to_f16", "apg_prefetch_hint", "apg_gemv_fused", "apg_gemv_fused_push", "apg_allreduce_finish",
     "apd_embed", "apd_attn_decode", "apd_lm_head", "apd_argmax_advance", "apd_argmax_advance_tp",
     "apd_sample_topk_advance", "apg_plan_fast",
+    "apg_persist_job_bytes", "apg_persist_smem", "apg_persist_job_gemv", "apg_persist_job_attn", "apg_persist_job_pack",
+    "apg_persist_job_reduce", "apg_persist_launch",
 )
 
 
@@ -144,6 +147,20 @@ def lib() -> ctypes.CDLL:
     L.apg_prefetch_hint.argtypes = [vp, ctypes.c_uint64]
     L.apg_round_f32_to_f16.restype = i32
     L.apg_round_f32_to_f16.argtypes = [vp, vp, u32, vp]
+    L.apg_persist_job_bytes.restype = u32
+    L.apg_persist_job_bytes.argtypes = []
+    L.apg_persist_smem.restype = i32
+    L.apg_persist_smem.argtypes = [i32, ctypes.POINTER(u32), ctypes.POINTER(u32)]
+    L.apg_persist_job_gemv.restype = i32
+    L.apg_persist_job_gemv.argtypes = [vp, u32, u32, i32, i32, u32, vp, vp, vp, vp, vp, vp, f32, vp, u32, u32, vp, u32, u32, u32]
+    L.apg_persist_job_attn.restype = i32
+    L.apg_persist_job_attn.argtypes = [vp, vp, vp, vp, vp, vp, vp, u32, u32, u32, f32, u32, u32]
+    L.apg_persist_job_pack.restype = i32
+    L.apg_persist_job_pack.argtypes = [vp, vp, vp, u32, u32, vp, vp, u32]
+    L.apg_persist_job_reduce.restype = i32
+    L.apg_persist_job_reduce.argtypes = [vp, vp, u32, u32, vp, vp, vp, u32, u32, u32]
+    L.apg_persist_launch.restype = i32
+    L.apg_persist_launch.argtypes = [vp, u32, i32, vp, vp, vp, vp, i32, u32, vp]
     _lib = L
     return L
 

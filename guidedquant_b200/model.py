@@ -34,21 +34,29 @@ MODEL_CONFIGS.setdefault("tiny128kv4", dict(dim=1024, n_layer=2, n_head=8, n_kv=
 class APTransformer:
     def __init__(self, model: str = "llama3-8b", bits: int = 2, max_seq_len: int = 256, device=None, pdl: bool = True,
                  norm_eps: float = 1e-5, n_layer: int | None = None, attn_splits: int | None = None,
-                 world_size: int = 1, rank: int = 0, process_group=None, glu_epilogue: bool = False,
+                 world_size: int = 1, rank: int = 0, process_group=None, glu_epilogue: bool | None = None,
                  engine: str | None = None):
         self.cfg = dict(MODEL_CONFIGS[model])
-        self.engine = engine or "launches"
-        assert self.engine in ("launches",), f"unknown decode engine {engine!r}"
+        # "persistent" (default): embedding + all blocks of a token are ONE cooperative launch of the persistent token
+        # kernel (persist.py / csrc/apgemv_persist.cuh), then lm_head + sampling; "launches": one PDL launch per op
+        self.engine = engine or ("persistent" if bits <= 4 else "launches")
+        assert self.engine in ("launches", "persistent"), f"unknown decode engine {engine!r}"
+        self.prog = None
         if n_layer is not None:
             self.cfg["n_layer"] = n_layer
         c = self.cfg
         assert c["dim"] // c["n_head"] == 128, "the attention kernel is specialised for head_dim 128"
         self.model, self.bits, self.S, self.eps = model, bits, max_seq_len, norm_eps
-        # EXPERIMENTAL (off by default, not yet measured on a GPU): keep w1w3's rows interleaved (gate_i, up_i) so that its
-        # epilogue writes silu(gate)*up once per element (apg_gemv_fused(silu_mul=2)) instead of every CTA of the w2 launch
-        # recomputing the activation in its prologue.  Same roundings -> same logits.  Single GPU only.
-        self.glu_epilogue = bool(glu_epilogue)
-        assert not (self.glu_epilogue and world_size > 1), "glu_epilogue is single-GPU only"
+        # w1w3's rows are kept interleaved (gate_i, up_i) so that its epilogue writes silu(gate)*up once per element instead
+        # of every CTA of the w2 launch recomputing the activation in its prologue: same roundings -> identical logits,
+        # measured 5 % faster per token on B200 (profiles/r2_ab_glu.log).  Always on in the persistent engine; in the
+        # launches engine it is the single-GPU default (its K-sharded w2 path keeps the prologue form).
+        if self.engine == "persistent":
+            assert glu_epilogue in (None, True), "the persistent engine always uses the SwiGLU epilogue"
+            self.glu_epilogue = True
+        else:
+            self.glu_epilogue = (world_size == 1) if glu_epilogue is None else bool(glu_epilogue)
+            assert not (self.glu_epilogue and world_size > 1), "glu_epilogue is single-GPU only in the launches engine"
         self.flags = _lib.APG_FLAG_PDL if pdl else 0
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
         self.rope_base = ROPE_BASE.get(model, 10000.0)
@@ -92,6 +100,7 @@ class APTransformer:
         self.v_cache = [torch.zeros((self.Hkv_l, max_seq_len, hd), dtype=f16, device=dev) for _ in range(c["n_layer"])]
         self.part = torch.zeros(self.H_l * self.nsplit * 132, dtype=torch.float32, device=dev) if self.nsplit > 1 else None
         self.graph = None
+        self.use_graph = True   # False: launch the token's kernels eagerly instead of replaying a captured CUDA graph
         self.stream = torch.cuda.Stream(device=dev)
         self.tok_host = torch.zeros(1, dtype=torch.int32).pin_memory()
         self.launches_per_token = 0
@@ -125,6 +134,7 @@ class APTransformer:
         if self.world > 1 or self.glu_epilogue:  # shard / re-order through the common path
             self.sd = {}
             self.load_state_dict(sd)
+        self.prog = self.graph = None
         return self
 
     def expected_keys(self) -> list[str]:
@@ -170,10 +180,11 @@ class APTransformer:
         for k in exp:
             t = self._shard(k, self._validate(k, sd[k]).to(self.device))
             if self.glu_epilogue and ".w1w3." in k:  # rows (gate | up) -> (gate_0, up_0, gate_1, up_1, ...)
-                inter = self.cfg["inter"]
+                inter = self.inter_l  # after sharding the rows are this rank's gate columns then its up columns
                 idx = torch.stack([torch.arange(inter), inter + torch.arange(inter)], dim=1).reshape(-1).to(t.device)
                 t = t.index_select(1 if k.endswith(".qweight") else 0, idx)
             self.sd[k] = t.contiguous()
+        self.prog = self.graph = None  # the job table / graph point into the old tensors
         return self
 
     def _shard(self, name: str, t: torch.Tensor) -> torch.Tensor:
@@ -260,11 +271,51 @@ class APTransformer:
         _lib.check(st, "apg_gemv_fused " + name)
         self.launches_per_token += 1
 
-    def decode_step(self):
-        """embedding -> L blocks -> lm_head -> greedy sample; reads self.token / self.pos on the device and advances them."""
+    def _build_program(self):
+        """the embedding row + every block of a token as ONE job list for the persistent token kernel (module docstring's
+        5 ops per block; K-sharded wo / w2 push their fp32 partial sums to every rank and are finished by a reduce job)"""
+        from .persist import PersistentProgram
+
+        c, sd, W = self.cfg, self.sd, self.world
+        prog = PersistentProgram(self.bits, self.device)
+        d = c["dim"]
+        X = [prog.buffer(d), prog.buffer(d)]
+        QKV, ATT = prog.buffer(self.lshapes["wqkv"][0]), prog.buffer(self.dk_l)
+        Hb, GU = prog.buffer(d), prog.buffer(self.inter_l)
+        scale = 1.0 / math.sqrt(128.0)
+        prog.pack(sd["tok_embeddings.weight"], X[0], row_index=self.token)
+        x = X[0]
+        nl = c["n_layer"]
+
+        def k_sharded(site, xin, name, out, residual, plain):
+            ptrs = [b + site * self.push.site_bytes for b in self.push.peer_base]
+            j = prog.gemv(xin, sd[name + ".qweight"], sd[name + ".lut"], None, push=(W, self.rank, ptrs))
+            prog.reduce(ptrs[self.rank], j, d, W, out, residual=residual, out_plain=plain)
+
+        for i in range(nl):
+            p = f"layers.{i}."
+            prog.gemv(x, sd[p + "attention.wqkv.qweight"], sd[p + "attention.wqkv.lut"], QKV, norm_w=sd[p + "input_layernorm.weight"],
+                      eps=self.eps)
+            prog.attn(QKV, self.inv_freq, self.k_cache[i], self.v_cache[i], ATT, self.H_l, self.Hkv_l, self.S, scale)
+            if W == 1:
+                prog.gemv(ATT, sd[p + "attention.wo.qweight"], sd[p + "attention.wo.lut"], Hb, residual=x)
+            else:
+                k_sharded(2 * i, ATT, p + "attention.wo", Hb, x, None)
+            prog.gemv(Hb, sd[p + "feed_forward.w1w3.qweight"], sd[p + "feed_forward.w1w3.lut"], GU,
+                      norm_w=sd[p + "post_attention_layernorm.weight"], eps=self.eps, glu=True)
+            xn = X[(i + 1) % 2]
+            plain = self.x if i == nl - 1 else None  # the fp16 hidden state the lm_head kernel reads
+            if W == 1:
+                prog.gemv(GU, sd[p + "feed_forward.w2.qweight"], sd[p + "feed_forward.w2.lut"], xn, residual=Hb, out_plain=plain)
+            else:
+                k_sharded(2 * i + 1, GU, p + "feed_forward.w2", xn, Hb, plain)
+            x = xn
+        self.prog = prog.finalize()
+
+    def _blocks_launches(self):
+        """launches engine: embedding + L blocks, 5 PDL launches per block"""
         L, c, sd, fl = _lib.lib(), self.cfg, self.sd, self.flags
         st = torch.cuda.current_stream().cuda_stream
-        self.launches_per_token = 0
         if "embed" not in self.debug_skip:
             _lib.check(L.apd_embed(sd["tok_embeddings.weight"].data_ptr(), self.token.data_ptr(), self.x.data_ptr(), c["dim"], c["vocab"], fl, st), "apd_embed")
             self.launches_per_token += 1
@@ -294,6 +345,19 @@ class APTransformer:
                                     n2, k2, self.bits, silu_mul=1, eps=self.eps, flags=fl)
                 self.push.finish(2 * i + 1, self.x, n2, residual=self.h, flags=fl)
                 self.launches_per_token += 4
+
+    def decode_step(self):
+        """embedding -> L blocks -> lm_head -> greedy sample; reads self.token / self.pos on the device and advances them."""
+        L, c, sd, fl = _lib.lib(), self.cfg, self.sd, self.flags
+        st = torch.cuda.current_stream().cuda_stream
+        self.launches_per_token = 0
+        if self.engine == "persistent":
+            if self.prog is None:
+                self._build_program()
+            self.prog.launch(self.pos)
+            self.launches_per_token = 1
+        else:
+            self._blocks_launches()
         if "lm_head" not in self.debug_skip:
           import ctypes
           npart = ctypes.c_uint32(0)
@@ -340,9 +404,14 @@ class APTransformer:
                 saved = (self.token.clone(), self.pos.clone())
                 self.decode_step()  # warm-up (function attributes, lazy init); its side effects are undone below
                 s.synchronize()
-                self.graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(self.graph, stream=s):
-                    self.decode_step()
+                if self.prog is not None:
+                    self.prog.check()  # a device-side watchdog would have fired on the very first token
+                if self.use_graph:
+                    self.graph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(self.graph, stream=s):
+                        self.decode_step()
+                else:
+                    self.graph = False  # eager: decode_step() per token (3 launches with the persistent engine)
                 self.token.copy_(saved[0])
                 self.pos.copy_(saved[1])
                 s.synchronize()
@@ -370,6 +439,12 @@ class APTransformer:
             self.capture()
         self._advance_host_pos()
         with torch.cuda.stream(self.stream):
+            self._replay()
+
+    def _replay(self):
+        if self.graph is False:
+            self.decode_step()
+        else:
             self.graph.replay()
 
     def step_host(self, token_host: torch.Tensor) -> int:
@@ -379,7 +454,7 @@ class APTransformer:
         self._advance_host_pos()
         with torch.cuda.stream(self.stream):
             self.token.copy_(token_host, non_blocking=True)
-            self.graph.replay()
+            self._replay()
             self.tok_host.copy_(self.token, non_blocking=True)
         self.stream.synchronize()
         return int(self.tok_host[0])

@@ -64,8 +64,11 @@ class ApGemvChain:
                  pdl: bool = True, world_size: int = 1, rank: int = 0, process_group=None, ctas_per_sm: int = 0,
                  l2_prefetch: bool = False, collective: str = "push", engine: str | None = None):
         self.cfg = dict(MODEL_CONFIGS[model])
-        self.engine = engine or "launches"
-        assert self.engine in ("launches",), f"unknown engine {engine!r}"
+        # "persistent": the whole chain is ONE cooperative launch of the persistent token kernel (persist.py);
+        # "launches": one PDL launch per Linear under a CUDA graph (the round-1 path)
+        self.engine = engine or ("persistent" if bits <= 4 and (world_size == 1 or collective == "push") else "launches")
+        assert self.engine in ("launches", "persistent"), f"unknown engine {engine!r}"
+        self.prog = None
         if n_layer is not None:
             self.cfg["n_layer"] = n_layer
         self.model, self.bits, self.pdl = model, bits, pdl
@@ -186,8 +189,53 @@ class ApGemvChain:
     def _view(t: torch.Tensor, a: int, n: int) -> torch.Tensor:
         return t.reshape(-1)[a:a + n].reshape(1, 1, n)
 
+    # ------------------------------------------------------------------ persistent engine
+    def _build_program(self):
+        """the same chain as _token() as one job list: x_in -> packets, 4*L GEMV jobs (K-sharded ones push their fp32
+        partial sums to every rank and are followed by a reduce job), last output also written as plain fp16"""
+        from .persist import PersistentProgram
+
+        prog = PersistentProgram(self.bits, self.device)
+        d, W = self.cfg["dim"], self.world
+        bx, qkv, o = prog.buffer(d), prog.buffer(self.shapes["wqkv"][0]), prog.buffer(d)
+        gu, hh = prog.buffer(self.shapes["w1w3"][0]), [prog.buffer(d), prog.buffer(d)]
+        self.y_dev = torch.zeros((1, 1, d), dtype=torch.float16, device=self.device)
+        prog.pack(self.x_in.reshape(1, d), bx)
+        x = bx
+        site = 0
+        nl = len(self.layers)
+
+        def lin(l, xin, out, plain=None):
+            nonlocal site
+            if not l.k_shard:
+                prog.gemv(xin, l.qweight, l.lut, out, out_plain=plain)
+                return
+            ptrs = [b + site * self.push.site_bytes for b in self.push.peer_base]
+            j = prog.gemv(xin, l.qweight, l.lut, None, push=(W, self.rank, ptrs))
+            prog.reduce(ptrs[self.rank], j, l.N, W, out, out_plain=plain)
+            site += 1
+
+        for li, (wqkv, wo, w1w3, w2) in enumerate(self.layers):
+            lin(wqkv, x, qkv)
+            lin(wo, qkv, o)
+            lin(w1w3, o, gu)
+            lin(w2, gu, hh[li % 2], plain=self.y_dev if li == nl - 1 else None)
+            x = hh[li % 2]
+        self.prog = prog.finalize()
+        self.launches_per_step = 1
+
     # ------------------------------------------------------------------ graph
     def capture(self):
+        if self.engine == "persistent":
+            with torch.cuda.device(self.device):
+                if self.prog is None:
+                    self._build_program()
+                with torch.cuda.stream(self.stream):
+                    self.prog.launch()  # warm-up (function attributes)
+                self.stream.synchronize()
+                self.prog.check()
+            self.graph = False  # a single launch per step: no graph needed
+            return self
         with torch.cuda.device(self.device):
             s = self.stream
             s.wait_stream(torch.cuda.current_stream())
@@ -205,6 +253,12 @@ class ApGemvChain:
         if self.graph is None:
             self.capture()
         with torch.cuda.stream(self.stream):
+            self._replay()
+
+    def _replay(self):
+        if self.engine == "persistent":
+            self.prog.launch()
+        else:
             self.graph.replay()
 
     def step_host(self, x_host: torch.Tensor) -> torch.Tensor:
@@ -213,7 +267,7 @@ class ApGemvChain:
             self.capture()
         with torch.cuda.stream(self.stream):
             self.x_in.copy_(x_host, non_blocking=True)
-            self.graph.replay()
+            self._replay()
             self.y_host.copy_(self.y_dev, non_blocking=True)
         self.stream.synchronize()
         return self.y_host
@@ -221,4 +275,9 @@ class ApGemvChain:
     def eager_token(self, x: torch.Tensor) -> torch.Tensor:
         """un-graphed reference execution of the same chain (for tests)."""
         self.x_in.copy_(x)
+        if self.engine == "persistent":
+            if self.prog is None:
+                self._build_program()
+            self.prog.launch()
+            return self.y_dev.clone()
         return self._token().clone()

@@ -142,6 +142,44 @@ int apg_dequant(const void *qweight, const void *lut, void *w_out,
 /* fp32 [n] -> fp16 [n] round-to-nearest-even; the epilogue of the K-sharded path after the fp32 all-reduce. */
 int apg_round_f32_to_f16(const float *in, void *out, uint32_t n, void *stream);
 
+/*
+ * ---------------------------------------------------------------------------------------------------------------
+ * Persistent token engine: ONE cooperative kernel launch runs a whole list of dependent jobs (the fused GEMVs of a decode
+ * step, the attention of every block, the embedding row, all-reduce finishers).  At batch 1 every Linear consumes the whole
+ * output vector of the previous one; as separate launches each of the ~160 hand-overs of a token costs ~3 us on B200 (PDL),
+ * inside this kernel activations travel as 8-byte (half2, tag) packets that consumers spin on — no grid barrier, no kernel
+ * boundary — while a producer thread per CTA keeps the packed weights of the NEXT Linears streaming into a shared-memory
+ * ring.  Replaces the reference's per-op launches of APLinear.forward + Inductor-fused glue under CUDA graphs
+ * (inference/generate.py:330-336, inference/model.py:151-167, 206-236, 261-285).  GEMV arithmetic is that of apg_gemv_fused.
+ *
+ * Usage: fill `n_jobs` descriptors of apg_persist_job_bytes() bytes each in HOST memory with apg_persist_job_*, copy the
+ * table to the device, then apg_persist_launch once per token.  "LL buffer" = device array of n/2 uint2 packets for a vector
+ * of n halfs (zero-initialised).  tag_* = index of the job that produces the packets being read / written (a job writes
+ * its own index); `sms` = SM count of the device that will run the table (rows are dealt to that many CTAs).
+ */
+uint32_t apg_persist_job_bytes(void);
+int apg_persist_smem(int bits, uint32_t *total_bytes, uint32_t *ring_bytes);
+/* flags: 1 = RMSNorm prologue (norm_w, norm_eps), 4 = residual add (LL buffer), 8 = SwiGLU epilogue (rows interleaved
+ * (gate_i, up_i), out has N/2 halfs), 16 = K-sharded push: fp32 partial sums + tag to slot `rank` of every rank's receive
+ * buffer peers[r] (uint2 [world][N]); bits 2..4, K % 128 == 0, K <= 32768, N even. */
+int apg_persist_job_gemv(void *job, uint32_t N, uint32_t K, int bits, int sms, uint32_t flags, const void *x, const void *qweight,
+                         const void *lut, void *out, void *out_plain, const void *norm_w, float norm_eps, const void *residual,
+                         uint32_t world, uint32_t rank, void *const *peers, uint32_t tag_x, uint32_t tag_res, uint32_t tag_out);
+/* RoPE + KV append at *pos + attention for head h on CTA h (Attention.forward, model.py:206-236); head_dim 128, H <= SMs */
+int apg_persist_job_attn(void *job, const void *qkv, const float *inv_freq, void *k_cache, void *v_cache, void *out, void *out_plain,
+                         uint32_t H, uint32_t Hkv, uint32_t S, float scale, uint32_t tag_x, uint32_t tag_out);
+/* out := packets of the fp16 row src_rows[clamp(*row_index)] (row 0 if row_index is NULL): tok_embeddings, model.py:123 */
+int apg_persist_job_pack(void *job, const void *src_rows, const int *row_index, uint32_t n, uint32_t n_rows, void *out, void *out_plain,
+                         uint32_t tag_out);
+/* out := fp16( sum over ranks of the fp32 packets in recv [world][N] ) + residual: finisher of a K-sharded push job */
+int apg_persist_job_reduce(void *job, const void *recv, uint32_t N, uint32_t world, const void *residual, void *out, void *out_plain,
+                           uint32_t tag_x, uint32_t tag_res, uint32_t tag_out);
+/* epoch: device uint32 token counter (zero-initialised; advanced by the launch when bump_epoch != 0); pos: device int
+ * position read by attention jobs; err_word: device uint32, non-zero after a launch = a device-side watchdog fired;
+ * done_counter: device uint32 scratch (zero).  flags bit 0: launch WITHOUT the cooperative attribute (debug). */
+int apg_persist_launch(const void *jobs_dev, uint32_t n_jobs, int bits, uint32_t *epoch, const int *pos, uint32_t *err_word,
+                       uint32_t *done_counter, int bump_epoch, uint32_t flags, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

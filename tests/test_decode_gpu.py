@@ -14,7 +14,7 @@ pytestmark = pytest.mark.gpu
 TOL = 2e-2
 
 
-def _build(model, bits, S, seed, nsplit=None):
+def _build(model, bits, S, seed, nsplit=None, engine=None):
     from guidedquant_b200.model import APTransformer
     from guidedquant_b200.runtime import MODEL_CONFIGS, linear_shapes
     from oracle import oracle as O
@@ -49,18 +49,19 @@ def _build(model, bits, S, seed, nsplit=None):
     out = (rng.standard_normal((cfg["vocab"], cfg["dim"])) / np.sqrt(cfg["dim"])).astype(f16)
     sd["output.weight"] = torch.from_numpy(out)
     dense["output.weight"] = torch.from_numpy(out.astype(np.float32))
-    m = APTransformer(model, bits=bits, max_seq_len=S, attn_splits=nsplit).load_state_dict(sd)
+    m = APTransformer(model, bits=bits, max_seq_len=S, attn_splits=nsplit, engine=engine).load_state_dict(sd)
     return m, dense, cfg
 
 
+@pytest.mark.parametrize("engine", ["persistent", "launches"])
 @pytest.mark.parametrize("model,bits,nsplit", [("golden-tiny", 2, None), ("golden-tiny", 4, None), ("tiny128", 3, None),
                                                 ("tiny128", 2, 4)])
-def test_decode_steps_match_oracle(model, bits, nsplit):
+def test_decode_steps_match_oracle(model, bits, nsplit, engine):
     from guidedquant_b200.model import ROPE_BASE
     from oracle.decode_oracle import DecodeOracle
 
     S = 32
-    m, dense, cfg = _build(model, bits, S, seed=3, nsplit=nsplit)
+    m, dense, cfg = _build(model, bits, S, seed=3, nsplit=nsplit, engine=engine)
     o = DecodeOracle(dense, cfg["n_layer"], cfg["n_head"], cfg["n_kv"], cfg["dim"], S, rope_base=ROPE_BASE[model], half_rounding=True)
     tokens = [1, 7, 100, 3, 55, 2, 9, 201]
     m.reset(tokens[0])
@@ -79,8 +80,9 @@ def test_decode_steps_match_oracle(model, bits, nsplit):
         assert int(m.token.cpu()[0]) == int(np.argmax(logits))   # greedy == argmax of its own logits, first index
 
 
-def test_generate_is_deterministic_and_graph_equals_eager():
-    m, dense, cfg = _build("tiny128", 2, 64, seed=5)
+@pytest.mark.parametrize("engine", ["persistent", "launches"])
+def test_generate_is_deterministic_and_graph_equals_eager(engine):
+    m, dense, cfg = _build("tiny128", 2, 64, seed=5, engine=engine)
     a = m.generate([1], 20)
     b = m.generate([1], 20)
     assert a == b and len(a) == 21 and a[0] == 1
@@ -91,6 +93,8 @@ def test_generate_is_deterministic_and_graph_equals_eager():
             m.decode_step()
     m.stream.synchronize()
     assert m.history[:21].cpu().tolist() == a
+    if m.prog is not None:
+        m.prog.check()
     # prompt longer than one token (sequential prefill)
     c = m.generate([1, 5, 9], 5)
     assert c[:3] == [1, 5, 9] and len(c) == 8
