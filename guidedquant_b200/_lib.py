@@ -150,7 +150,7 @@ def lib() -> ctypes.CDLL:
     L.apg_persist_job_bytes.restype = u32
     L.apg_persist_job_bytes.argtypes = []
     L.apg_persist_smem.restype = i32
-    L.apg_persist_smem.argtypes = [i32, ctypes.POINTER(u32), ctypes.POINTER(u32)]
+    L.apg_persist_smem.argtypes = [i32, u32, ctypes.POINTER(u32), ctypes.POINTER(u32)]
     L.apg_persist_job_gemv.restype = i32
     L.apg_persist_job_gemv.argtypes = [vp, u32, u32, i32, i32, u32, vp, vp, vp, vp, vp, vp, f32, vp, u32, u32, vp, u32, u32, u32]
     L.apg_persist_job_attn.restype = i32
@@ -160,7 +160,7 @@ def lib() -> ctypes.CDLL:
     L.apg_persist_job_reduce.restype = i32
     L.apg_persist_job_reduce.argtypes = [vp, vp, u32, u32, vp, vp, vp, u32, u32, u32]
     L.apg_persist_launch.restype = i32
-    L.apg_persist_launch.argtypes = [vp, u32, i32, vp, vp, vp, vp, i32, u32, vp]
+    L.apg_persist_launch.argtypes = [vp, u32, i32, u32, vp, vp, vp, vp, i32, u32, vp, vp]
     _lib = L
     return L
 

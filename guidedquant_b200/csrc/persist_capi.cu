@@ -14,7 +14,7 @@ namespace {
 
 inline bool al(const void *p, uintptr_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
 
-constexpr uint32_t kSmemTotal = 227u * 1024u - 1024u;  // dynamic part; 1 KB is left for the kernel's static shared header (PkShared)
+constexpr uint32_t kSmemTotal = 227u * 1024u - 2048u;  // dynamic part; 2 KB are left for the kernel's static shared header (PkShared)
 
 template <int BITS>
 constexpr uint32_t ring_rel() {
@@ -56,10 +56,12 @@ extern "C" {
 
 uint32_t apg_persist_job_bytes(void) { return (uint32_t)sizeof(apg::PJob); }
 
-int apg_persist_smem(int bits, uint32_t *total_bytes, uint32_t *ring_bytes) {
+int apg_persist_smem(int bits, uint32_t max_k, uint32_t *total_bytes, uint32_t *ring_bytes) {
     if (bits < 2 || bits > 4) return APG_ERR_UNSUPPORTED;
+    const uint32_t xs = (2u * max_k + 1023u) & ~1023u;
+    if (ring_rel_bits(bits) + xs + 2u * apg::PK_MAX_STAGE > kSmemTotal) return APG_ERR_UNSUPPORTED;
     if (total_bytes) *total_bytes = kSmemTotal;
-    if (ring_bytes) *ring_bytes = (kSmemTotal - ring_rel_bits(bits)) & ~1023u;
+    if (ring_bytes) *ring_bytes = (kSmemTotal - ring_rel_bits(bits) - xs) & ~1023u;
     return APG_OK;
 }
 
@@ -81,21 +83,19 @@ int apg_persist_job_gemv(void *job, uint32_t N, uint32_t K, int bits, int sms, u
     memset(&jb, 0, sizeof(jb));
     jb.type = PJ_GEMV, jb.flags = flags, jb.N = N, jb.K = K;
     const uint32_t nchunk = (K + 1023u) / 1024u;
-    jb.cpw = nchunk > 8u ? 2u : 1u;
-    jb.nwk = (nchunk + jb.cpw - 1) / jb.cpw;          // <= 16
+    if (nchunk > PK_NCW) return APG_ERR_UNSUPPORTED;  // one 1024-chunk per consumer warp: K <= 16384
+    jb.cpw = 1u;
+    jb.nwk = nchunk;                                  // <= 16
     jb.groups = PK_NCW / jb.nwk;                      // >= 1
     jb.inv_nwk = (65536u + jb.nwk - 1) / jb.nwk;
     const uint32_t row_bytes = K / 8u * (uint32_t)bits;
-    uint32_t rs = 8;
-    while (rs > 2 && rs * row_bytes > PK_MAX_STAGE) rs >>= 1;
+    uint32_t rs = 8;                                  // rows per stage: 8, or 4 when 8 rows exceed a 32 KB stage
+    if (rs * row_bytes > PK_MAX_STAGE) rs = 4;
     if (rs * row_bytes > PK_MAX_STAGE) return APG_ERR_UNSUPPORTED;
     jb.rs = rs;
     jb.stage_bytes = rs * row_bytes;
-    if (flags & PF_NORM) {
-        if (jb.cpw != 1) return APG_ERR_UNSUPPORTED;  // the fused RMSNorm keeps one chunk per warp (K <= 8192)
-    }
     if (flags & PF_GLU) {
-        if (jb.cpw != 1 || rs != 8 || (N & 3u) || (flags & (PF_RESIDUAL | PF_PUSH))) return APG_ERR_UNSUPPORTED;
+        if ((N & 3u) || (flags & (PF_RESIDUAL | PF_PUSH))) return APG_ERR_UNSUPPORTED;
     }
     if (flags & PF_PUSH) {
         if (world < 2 || world > 8 || rank >= world || !peers || (flags & PF_RESIDUAL)) return APG_ERR_MODE;
@@ -105,7 +105,7 @@ int apg_persist_job_gemv(void *job, uint32_t N, uint32_t K, int bits, int sms, u
         }
         jb.world = world, jb.rank = rank;
     }
-    jb.unit_rows = (flags & PF_GLU) ? 4u : (rs / 2u > 2u ? rs / 2u : 2u);
+    jb.unit_rows = (flags & PF_GLU) ? 4u : rs / 2u;   // 4 or 2 rows: even, so an output packet never straddles two CTAs
     const uint32_t tot_units = (N + jb.unit_rows - 1) / jb.unit_rows;
     jb.units_q = tot_units / (uint32_t)sms, jb.units_rem = tot_units % (uint32_t)sms;
     const uint32_t units_per_cta = (tot_units + sms - 1) / sms;
@@ -118,17 +118,17 @@ int apg_persist_job_gemv(void *job, uint32_t N, uint32_t K, int bits, int sms, u
     return APG_OK;
 }
 
-int apg_persist_job_attn(void *job, const void *qkv, const float *inv_freq, void *k_cache, void *v_cache, void *out, void *out_plain,
+int apg_persist_job_attn(void *job, const void *qkv, const void *rope_cs, void *k_cache, void *v_cache, void *out, void *out_plain,
                          uint32_t H, uint32_t Hkv, uint32_t S, float scale, uint32_t tag_x, uint32_t tag_out) {
     using namespace apg;
-    if (!job || !qkv || !inv_freq || !k_cache || !v_cache || !out) return APG_ERR_NULL;
+    if (!job || !qkv || !rope_cs || !k_cache || !v_cache || !out) return APG_ERR_NULL;
     if (H == 0 || Hkv == 0 || H % Hkv || S == 0) return APG_ERR_SHAPE;
     if (!al(qkv, 16) || !al(k_cache, 16) || !al(v_cache, 16) || !al(out, 16) || (out_plain && !al(out_plain, 8))) return APG_ERR_ALIGN;
     PJob jb;
     memset(&jb, 0, sizeof(jb));
     jb.type = PJ_ATTN, jb.a0 = H, jb.a1 = Hkv, jb.a2 = S, jb.f0 = scale;
     jb.x = qkv, jb.out = out, jb.out_plain = out_plain;
-    jb.p0 = const_cast<float *>(inv_freq), jb.p1 = k_cache, jb.p2 = v_cache;
+    jb.p0 = const_cast<void *>(rope_cs), jb.p1 = k_cache, jb.p2 = v_cache;
     jb.tag_x = tag_x, jb.tag_out = tag_out;
     memcpy(job, &jb, sizeof(jb));
     return APG_OK;
@@ -164,8 +164,8 @@ int apg_persist_job_reduce(void *job, const void *recv, uint32_t N, uint32_t wor
     return APG_OK;
 }
 
-int apg_persist_launch(const void *jobs_dev, uint32_t n_jobs, int bits, uint32_t *epoch, const int *pos, uint32_t *err_word,
-                       uint32_t *done_counter, int bump_epoch, uint32_t flags, void *stream) {
+int apg_persist_launch(const void *jobs_dev, uint32_t n_jobs, int bits, uint32_t max_k, uint32_t *epoch, const int *pos,
+                       uint32_t *err_word, uint32_t *done_counter, int bump_epoch, uint32_t flags, void *prof, void *stream) {
     if (!jobs_dev || !epoch || !err_word || !done_counter) return APG_ERR_NULL;
     if (bits < 2 || bits > 4) return APG_ERR_UNSUPPORTED;
     if (n_jobs == 0) return APG_ERR_SHAPE;
@@ -177,8 +177,11 @@ int apg_persist_launch(const void *jobs_dev, uint32_t n_jobs, int bits, uint32_t
     apg::PParams p;
     p.jobs = static_cast<const apg::PJob *>(jobs_dev);
     p.n_jobs = n_jobs;
-    p.ring_bytes = (kSmemTotal - ring_rel_bits(bits)) & ~1023u;
+    p.xs_bytes = (2u * max_k + 1023u) & ~1023u;  // staging area of a job's input vector
+    if (max_k < 128u || ring_rel_bits(bits) + p.xs_bytes + 2u * apg::PK_MAX_STAGE > kSmemTotal) return APG_ERR_UNSUPPORTED;
+    p.ring_bytes = (kSmemTotal - ring_rel_bits(bits) - p.xs_bytes) & ~1023u;
     p.epoch = epoch, p.pos = pos, p.err = err_word, p.done = done_counter, p.bump_epoch = bump_epoch ? 1u : 0u;
+    p.prof = static_cast<long long *>(prof);
     const bool coop = !(flags & 1u);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (bits == 2) return launch_bits<2>(p, sms, coop, s);

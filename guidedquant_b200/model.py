@@ -22,7 +22,7 @@ import math
 import torch
 
 from . import _lib
-from .runtime import MODEL_CONFIGS, gemv_algo_bytes, linear_shapes
+from .runtime import MODEL_CONFIGS, gemv_algo_bytes, linear_shapes, persistent_supported
 
 ROPE_BASE = {"llama3-8b": 500000.0, "llama3-70b": 500000.0, "llama2-7b": 10000.0, "llama2-70b": 10000.0, "tiny": 500000.0,
              "golden-tiny": 500000.0, "tiny128": 500000.0, "tiny128kv4": 500000.0}
@@ -37,9 +37,10 @@ class APTransformer:
                  world_size: int = 1, rank: int = 0, process_group=None, glu_epilogue: bool | None = None,
                  engine: str | None = None):
         self.cfg = dict(MODEL_CONFIGS[model])
-        # "persistent" (default): embedding + all blocks of a token are ONE cooperative launch of the persistent token
-        # kernel (persist.py / csrc/apgemv_persist.cuh), then lm_head + sampling; "launches": one PDL launch per op
-        self.engine = engine or ("persistent" if bits <= 4 else "launches")
+        # "persistent" (default under tensor parallelism): embedding + all blocks of a token are ONE cooperative launch of
+        # the persistent token kernel (persist.py / csrc/apgemv_persist.cuh), then lm_head + sampling;
+        # "launches" (default on one GPU, measured faster there): one PDL launch per op
+        self.engine = engine or ("persistent" if world_size > 1 and persistent_supported(self.cfg, bits, world_size) else "launches")
         assert self.engine in ("launches", "persistent"), f"unknown decode engine {engine!r}"
         self.prog = None
         if n_layer is not None:
@@ -283,6 +284,9 @@ class APTransformer:
         QKV, ATT = prog.buffer(self.lshapes["wqkv"][0]), prog.buffer(self.dk_l)
         Hb, GU = prog.buffer(d), prog.buffer(self.inter_l)
         scale = 1.0 / math.sqrt(128.0)
+        # cos / sin of every position in fp32, rounded to fp16 like the reference's rotary embedding (model.py:396-405)
+        ang = torch.arange(self.S, dtype=torch.float32, device=self.device)[:, None] * self.inv_freq[None, :].float()
+        rope_cs = torch.cat([torch.cos(ang), torch.sin(ang)], dim=1).half().contiguous()
         prog.pack(sd["tok_embeddings.weight"], X[0], row_index=self.token)
         x = X[0]
         nl = c["n_layer"]
@@ -296,7 +300,7 @@ class APTransformer:
             p = f"layers.{i}."
             prog.gemv(x, sd[p + "attention.wqkv.qweight"], sd[p + "attention.wqkv.lut"], QKV, norm_w=sd[p + "input_layernorm.weight"],
                       eps=self.eps)
-            prog.attn(QKV, self.inv_freq, self.k_cache[i], self.v_cache[i], ATT, self.H_l, self.Hkv_l, self.S, scale)
+            prog.attn(QKV, rope_cs, self.k_cache[i], self.v_cache[i], ATT, self.H_l, self.Hkv_l, self.S, scale)
             if W == 1:
                 prog.gemv(ATT, sd[p + "attention.wo.qweight"], sd[p + "attention.wo.lut"], Hb, residual=x)
             else:

@@ -9,7 +9,7 @@ dependent steps of a token (the reference runs one launch per op under torch.com
     x = prog.buffer(dim); qkv = prog.buffer(n_qkv) ...
     prog.pack(src_rows, x, row_index=token)                    # x := emb[token]
     prog.gemv(x, qweight, lut, qkv, norm_w=w, eps=1e-5)        # qkv := W . rmsnorm(x)
-    prog.attn(qkv, inv_freq, k_cache, v_cache, att, H, Hkv, S, scale)
+    prog.attn(qkv, rope_cs, k_cache, v_cache, att, H, Hkv, S, scale)
     ...
     prog.finalize(); prog.launch(pos)                          # per token (CUDA-graph capturable)
 """
@@ -48,11 +48,13 @@ class PersistentProgram:
         self.host = bytearray()
         self.n_jobs = 0
         self.n_gemv = 0
+        self.max_k = 128                # largest GEMV input length: sizes the kernel's shared-memory x staging
         self.keep: list = []            # tensors the job table points to
         self.jobs_dev: torch.Tensor | None = None
         self.epoch = torch.zeros(2, dtype=torch.int32, device=self.device)   # token counter (packets carry epoch*n_jobs + job)
         self.err = torch.zeros(1, dtype=torch.int32, device=self.device)     # watchdog word
         self.done = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.prof: torch.Tensor | None = None   # enable_profile(): int64 [SMs, n_jobs, 4] clock stamps of the last launch
 
     # ------------------------------------------------------------------ buffers
     def buffer(self, n_halfs: int) -> LLBuf:
@@ -100,19 +102,21 @@ class PersistentProgram:
         _lib.check(st, f"apg_persist_job_gemv N={N} K={K} bits={bits}")
         self.keep += [qweight, lut, norm_w, out_plain]
         self.n_gemv += 1
+        self.max_k = max(self.max_k, K)
         if out is not None:
             out.tag = idx
         return self._append(raw)
 
-    def attn(self, qkv: LLBuf, inv_freq: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tensor, out: LLBuf, H: int, Hkv: int,
+    def attn(self, qkv: LLBuf, rope_cs: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tensor, out: LLBuf, H: int, Hkv: int,
              S: int, scale: float, out_plain: torch.Tensor | None = None) -> int:
         assert qkv.tag is not None and H <= self.sms, "one CTA per head"
+        assert rope_cs.dtype == torch.float16 and tuple(rope_cs.shape) == (S, 128) and rope_cs.is_contiguous()
         raw = (ctypes.c_uint8 * self.job_bytes)()
         idx = self.n_jobs
-        st = self.L.apg_persist_job_attn(raw, qkv.ptr(), inv_freq.data_ptr(), k_cache.data_ptr(), v_cache.data_ptr(), out.ptr(),
+        st = self.L.apg_persist_job_attn(raw, qkv.ptr(), rope_cs.data_ptr(), k_cache.data_ptr(), v_cache.data_ptr(), out.ptr(),
                                          self._p(out_plain), H, Hkv, S, float(scale), qkv.tag, idx)
         _lib.check(st, "apg_persist_job_attn")
-        self.keep += [inv_freq, k_cache, v_cache, out_plain]
+        self.keep += [rope_cs, k_cache, v_cache, out_plain]
         out.tag = idx
         return self._append(raw)
 
@@ -144,17 +148,23 @@ class PersistentProgram:
     # ------------------------------------------------------------------ run
     def finalize(self):
         assert self.n_jobs > 0
-        self.jobs_dev = torch.frombuffer(bytes(self.host), dtype=torch.uint8).clone().to(self.device)
+        self.jobs_dev = torch.frombuffer(bytearray(self.host), dtype=torch.uint8).clone().to(self.device)
         return self
 
     def launch(self, pos: torch.Tensor | None = None, bump_epoch: bool = True, cooperative: bool = True):
         """one launch = one pass over the job list; asynchronous on the current stream, CUDA-graph capturable"""
         if self.jobs_dev is None:
             self.finalize()
-        st = self.L.apg_persist_launch(self.jobs_dev.data_ptr(), self.n_jobs, self.bits, self.epoch.data_ptr(),
+        st = self.L.apg_persist_launch(self.jobs_dev.data_ptr(), self.n_jobs, self.bits, self.max_k, self.epoch.data_ptr(),
                                        pos.data_ptr() if pos is not None else None, self.err.data_ptr(), self.done.data_ptr(),
-                                       1 if bump_epoch else 0, 0 if cooperative else 1, torch.cuda.current_stream().cuda_stream)
+                                       1 if bump_epoch else 0, 0 if cooperative else 1,
+                                       self.prof.data_ptr() if self.prof is not None else None, torch.cuda.current_stream().cuda_stream)
         _lib.check(st, "apg_persist_launch")
+
+    def enable_profile(self):
+        """debug aid: per-CTA, per-job clock64 stamps (job start, x in registers, stages done, job end) of every launch"""
+        self.prof = torch.zeros((self.sms, self.n_jobs, 4), dtype=torch.int64, device=self.device)
+        return self
 
     def check(self):
         """synchronising: raise if a device-side watchdog fired (a wait that never completed)"""

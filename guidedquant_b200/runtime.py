@@ -44,6 +44,18 @@ def linear_shapes(cfg: dict) -> dict:
     }
 
 
+def persistent_supported(cfg: dict, bits: int, world: int = 1) -> bool:
+    """the persistent token kernel takes K <= 16384 per GEMV job (one 1024-chunk per consumer warp) with 4 rows of all planes
+    within a 32 KB stage; Llama-70B's w2 (K = 28672) on ONE GPU does not fit and runs on the per-launch engine"""
+    if bits < 2 or bits > 4:
+        return False
+    for name, (N, K) in linear_shapes(cfg).items():
+        k_local = K // world if name in ("wo", "w2") else K
+        if k_local > 16384 or k_local % 128 or 4 * (k_local // 8) * bits > 32768:
+            return False
+    return True
+
+
 def gemv_algo_bytes(N: int, K: int, bits: int, M: int = 1) -> int:
     """algorithmic bytes of one GEMV call: planes + LUT + x + y."""
     return bits * N * K // 8 + N * (1 << bits) * 2 + M * K * 2 + M * N * 2
@@ -66,7 +78,11 @@ class ApGemvChain:
         self.cfg = dict(MODEL_CONFIGS[model])
         # "persistent": the whole chain is ONE cooperative launch of the persistent token kernel (persist.py);
         # "launches": one PDL launch per Linear under a CUDA graph (the round-1 path)
-        self.engine = engine or ("persistent" if bits <= 4 and (world_size == 1 or collective == "push") else "launches")
+        # default: per-launch kernels on one GPU (measured faster there: the hand-over between two Linears costs about the
+        # same either way and the per-launch kernel keeps 18 warps per SM busy); the persistent kernel under
+        # tensor parallelism, where the per-GPU Linears are small and the launch count is what bounds a token
+        ok = world_size > 1 and collective == "push" and persistent_supported(self.cfg, bits, world_size)
+        self.engine = engine or ("persistent" if ok else "launches")
         assert self.engine in ("launches", "persistent"), f"unknown engine {engine!r}"
         self.prog = None
         if n_layer is not None:

@@ -158,15 +158,17 @@ int apg_round_f32_to_f16(const float *in, void *out, uint32_t n, void *stream);
  * its own index); `sms` = SM count of the device that will run the table (rows are dealt to that many CTAs).
  */
 uint32_t apg_persist_job_bytes(void);
-int apg_persist_smem(int bits, uint32_t *total_bytes, uint32_t *ring_bytes);
+/* shared-memory budget for a job list whose largest GEMV input has max_k elements (dynamic bytes, weight-ring bytes) */
+int apg_persist_smem(int bits, uint32_t max_k, uint32_t *total_bytes, uint32_t *ring_bytes);
 /* flags: 1 = RMSNorm prologue (norm_w, norm_eps), 4 = residual add (LL buffer), 8 = SwiGLU epilogue (rows interleaved
  * (gate_i, up_i), out has N/2 halfs), 16 = K-sharded push: fp32 partial sums + tag to slot `rank` of every rank's receive
- * buffer peers[r] (uint2 [world][N]); bits 2..4, K % 128 == 0, K <= 32768, N even. */
+ * buffer peers[r] (uint2 [world][N]); bits 2..4, K % 128 == 0, K <= 16384, 4 rows of all planes <= 32 KB, N even. */
 int apg_persist_job_gemv(void *job, uint32_t N, uint32_t K, int bits, int sms, uint32_t flags, const void *x, const void *qweight,
                          const void *lut, void *out, void *out_plain, const void *norm_w, float norm_eps, const void *residual,
                          uint32_t world, uint32_t rank, void *const *peers, uint32_t tag_x, uint32_t tag_res, uint32_t tag_out);
-/* RoPE + KV append at *pos + attention for head h on CTA h (Attention.forward, model.py:206-236); head_dim 128, H <= SMs */
-int apg_persist_job_attn(void *job, const void *qkv, const float *inv_freq, void *k_cache, void *v_cache, void *out, void *out_plain,
+/* RoPE + KV append at *pos + attention for head h on CTA h (Attention.forward, model.py:206-236); head_dim 128, H <= SMs;
+ * rope_cs: fp16 [S][128] = cos(pos * inv_freq[0..63]) | sin(...) computed in fp32 and rounded (model.py:396-405) */
+int apg_persist_job_attn(void *job, const void *qkv, const void *rope_cs, void *k_cache, void *v_cache, void *out, void *out_plain,
                          uint32_t H, uint32_t Hkv, uint32_t S, float scale, uint32_t tag_x, uint32_t tag_out);
 /* out := packets of the fp16 row src_rows[clamp(*row_index)] (row 0 if row_index is NULL): tok_embeddings, model.py:123 */
 int apg_persist_job_pack(void *job, const void *src_rows, const int *row_index, uint32_t n, uint32_t n_rows, void *out, void *out_plain,
@@ -175,10 +177,11 @@ int apg_persist_job_pack(void *job, const void *src_rows, const int *row_index, 
 int apg_persist_job_reduce(void *job, const void *recv, uint32_t N, uint32_t world, const void *residual, void *out, void *out_plain,
                            uint32_t tag_x, uint32_t tag_res, uint32_t tag_out);
 /* epoch: device uint32 token counter (zero-initialised; advanced by the launch when bump_epoch != 0); pos: device int
- * position read by attention jobs; err_word: device uint32, non-zero after a launch = a device-side watchdog fired;
- * done_counter: device uint32 scratch (zero).  flags bit 0: launch WITHOUT the cooperative attribute (debug). */
-int apg_persist_launch(const void *jobs_dev, uint32_t n_jobs, int bits, uint32_t *epoch, const int *pos, uint32_t *err_word,
-                       uint32_t *done_counter, int bump_epoch, uint32_t flags, void *stream);
+ * position read by attention jobs; max_k: largest K over the GEMV jobs (sizes the shared-memory x staging); err_word: device uint32, non-zero after a launch = a device-side watchdog fired;
+ * done_counter: device uint32 scratch (zero).  flags bit 0: launch WITHOUT the cooperative attribute (debug).
+ * prof: NULL, or device int64 [SMs][n_jobs][4] receiving clock64 stamps per CTA and job (start, x loaded, stages done, end). */
+int apg_persist_launch(const void *jobs_dev, uint32_t n_jobs, int bits, uint32_t max_k, uint32_t *epoch, const int *pos,
+                       uint32_t *err_word, uint32_t *done_counter, int bump_epoch, uint32_t flags, void *prof, void *stream);
 
 #ifdef __cplusplus
 }

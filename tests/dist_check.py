@@ -108,32 +108,37 @@ def main():
         from guidedquant_b200.model import APTransformer
 
         tpm = "tiny128" if world == 2 else "tiny128kv4"   # kv heads must divide by the world size
-        full = APTransformer(tpm, bits=2, max_seq_len=32).random_init(seed=11)
-        sd_full = {k: v.clone() for k, v in full.sd.items()}
-        tp = APTransformer(tpm, bits=2, max_seq_len=32, world_size=world, rank=rank, process_group=dist.group.WORLD)
-        tp.load_state_dict(sd_full)
-        full.reset(1)
-        tp.reset(1)
-        worst = 0.0
-        for pos, tok in enumerate([1, 9, 77, 5, 300, 2]):
-            for m in (full, tp):
-                m.token.fill_(tok)
-                m.step()
-                m.stream.synchronize()
-            vl = tp.V_l   # lm_head is vocab-sharded: compare this rank's slice
-            a, b = full.logits.float()[rank * vl:(rank + 1) * vl], tp.logits.float()
-            assert int(tp.token.cpu()[0]) == int(full.token.cpu()[0]) or err_margin(full.logits.float()), "greedy token differs"
-            err = float((a - b).abs().max() / a.abs().max())
-            worst = max(worst, err)
-            assert err <= 1e-2, (pos, err)
-        toks_tp = tp.generate([1], 12)
-        toks_all = [None] * world
-        dist.all_gather_object(toks_all, toks_tp)
-        assert all(t == toks_all[0] for t in toks_all), "ranks generated different tokens"
-        log("TP decode vs single GPU: worst logit err", worst, "tokens", toks_tp[:8])
-        tp.graph = None
-        full.graph = None
-        del tp, full
+        src = APTransformer(tpm, bits=2, max_seq_len=32, engine="launches", glu_epilogue=False).random_init(seed=11)
+        sd_full = {k: v.clone() for k, v in src.sd.items()}   # the reference (unsharded, un-permuted) layout
+        del src
+        for engine in ("persistent", "launches"):
+            full = APTransformer(tpm, bits=2, max_seq_len=32, engine=engine).load_state_dict(sd_full)
+            tp = APTransformer(tpm, bits=2, max_seq_len=32, world_size=world, rank=rank, process_group=dist.group.WORLD, engine=engine)
+            tp.load_state_dict(sd_full)
+            full.reset(1)
+            tp.reset(1)
+            worst = 0.0
+            for pos, tok in enumerate([1, 9, 77, 5, 300, 2]):
+                for m in (full, tp):
+                    m.token.fill_(tok)
+                    m.step()
+                    m.stream.synchronize()
+                vl = tp.V_l   # lm_head is vocab-sharded: compare this rank's slice
+                a, b = full.logits.float()[rank * vl:(rank + 1) * vl], tp.logits.float()
+                assert int(tp.token.cpu()[0]) == int(full.token.cpu()[0]) or err_margin(full.logits.float()), "greedy token differs"
+                err = float((a - b).abs().max() / a.abs().max())
+                worst = max(worst, err)
+                assert err <= 1e-2, (engine, pos, err)
+            toks_tp = tp.generate([1], 12)
+            if tp.prog is not None:
+                tp.prog.check()
+            toks_all = [None] * world
+            dist.all_gather_object(toks_all, toks_tp)
+            assert all(t == toks_all[0] for t in toks_all), "ranks generated different tokens"
+            log(f"TP decode ({engine} engine) vs single GPU: worst logit err", worst, "tokens", toks_tp[:8])
+            tp.graph = None
+            full.graph = None
+            del tp, full
         if rank == 0:
             print("sharded ApGemvChain: graph == eager, all ranks agree", flush=True)
         # a live CUDA graph that captured NCCL kernels makes communicator teardown hang: drop it first

@@ -14,9 +14,108 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("model,bits,layers", [("llama3-8b", 2, 2), ("llama3-8b", 3, 1), ("llama3-8b", 4, 1), ("llama2-70b", 2, 1),
-                                                ("llama2-70b", 4, 1), ("tiny", 2, 2), ("llama2-7b", 3, 1)])
-def test_chain_bit_identical_to_launch_engine(model, bits, layers):
+TOL_TRUTH = 1.2e-3
+
+
+def _f64(q, lut, x, bits):
+    from guidedquant_b200 import ap_gemv
+
+    W = ap_gemv.anyprec_dequant(q, lut, bits)
+    out = torch.empty(W.shape[0], dtype=torch.float64, device=W.device)
+    step = max(1, (1 << 27) // W.shape[1])
+    for r0 in range(0, W.shape[0], step):
+        out[r0:r0 + step] = (W[r0:r0 + step].double() @ x.double().reshape(-1, 1)).reshape(-1)
+    return out
+
+
+def _persist_gemv(q, lut, x, bits, norm_w=None, residual=None, glu=False):
+    """ONE fused GEMV job through the persistent kernel: pack(x) [+ pack(residual)] -> gemv -> plain fp16 output"""
+    from guidedquant_b200.persist import PersistentProgram
+
+    N, K = q.shape[1], q.shape[2] * 32
+    prog = PersistentProgram(bits)
+    X = prog.buffer(K)
+    prog.pack(x.reshape(1, K).contiguous(), X)
+    R = None
+    if residual is not None:
+        R = prog.buffer(N)
+        prog.pack(residual.reshape(1, N).contiguous(), R)
+    n_out = N // 2 if glu else N
+    Y = prog.buffer(n_out)
+    out = torch.full((n_out,), float("nan"), dtype=torch.float16, device="cuda")
+    prog.gemv(X, q, lut, Y, norm_w=norm_w, residual=R, glu=glu, out_plain=out)
+    for _ in range(3):  # repeated launches: tags advance
+        prog.launch()
+    torch.cuda.synchronize()
+    prog.check()
+    return out
+
+
+@pytest.mark.parametrize("bits", [2, 3, 4])
+@pytest.mark.parametrize("N,K", [(4096, 4096), (6144, 4096), (28672, 4096), (4096, 14336), (10240, 8192), (8192, 8192),
+                                 (8192, 3584), (4096, 11008), (100, 1024), (2, 128), (1026, 2176)])
+def test_persistent_gemv_job_vs_f64_and_launch_kernel(N, K, bits):
+    """a single GEMV job of the persistent kernel at the benchmark shapes (and ragged ones): within the stated tolerance of the
+    fp64 truth, and BIT-IDENTICAL to the per-launch kernel whenever that one also runs one K chunk per warp (K <= 8192)."""
+    from guidedquant_b200 import ap_gemv
+
+    g = torch.Generator(device="cuda").manual_seed(N + K + bits)
+    q = torch.randint(-2**31, 2**31 - 1, (bits, N, K // 32), dtype=torch.int32, device="cuda", generator=g)
+    lut = (torch.randn((N, 1 << bits), device="cuda", generator=g) * 0.02).half()
+    x = torch.randn((1, 1, K), device="cuda", generator=g).half()
+    y = _persist_gemv(q, lut, x, bits)
+    assert not torch.isnan(y).any()
+    y64 = _f64(q, lut, x, bits)
+    err = float((y.double() - y64).abs().max() / y64.abs().max())
+    assert err <= (TOL_TRUTH if N * K >= 65536 else 2.5e-3), (N, K, bits, err)   # tiny cases: max-norm over a handful of outputs
+    yl = torch.empty((1, 1, N), dtype=torch.float16, device="cuda")
+    ap_gemv.anyprec_gemv(x, yl, q, lut, bits)
+    if K <= 8192 and K % 128 == 0:
+        assert torch.equal(yl.reshape(-1).view(torch.int16), y.view(torch.int16)), (N, K, bits)
+    else:
+        assert float((yl.reshape(-1).float() - y.float()).abs().max() / y64.abs().max()) <= 1e-3
+
+
+@pytest.mark.parametrize("bits", [2, 4])
+@pytest.mark.parametrize("variant", ["norm", "residual", "norm+residual", "glu", "norm+glu"])
+def test_persistent_fused_variants(variant, bits):
+    """fused RMSNorm prologue, residual epilogue and SwiGLU epilogue of the GEMV job vs a torch restatement with the reference's
+    fp16 roundings (inference/model.py:151-167, 261-285) on the fp64 Linear."""
+    N, K = 28672, 4096
+    g = torch.Generator(device="cuda").manual_seed(7 * bits + len(variant))
+    q = torch.randint(-2**31, 2**31 - 1, (bits, N, K // 32), dtype=torch.int32, device="cuda", generator=g)
+    lut = (torch.randn((N, 1 << bits), device="cuda", generator=g) * 0.02).half()
+    x = torch.randn((K,), device="cuda", generator=g).half()
+    norm_w = (1 + 0.1 * torch.randn(K, device="cuda", generator=g)).half() if "norm" in variant else None
+    glu = "glu" in variant
+    res = torch.randn(N, device="cuda", generator=g).half() if "residual" in variant else None
+    y = _persist_gemv(q, lut, x, bits, norm_w=norm_w, residual=res, glu=glu)
+    xe = x
+    if norm_w is not None:
+        xf = x.float()
+        xe = (xf * torch.rsqrt((xf * xf).mean() + 1e-5)).half() * norm_w
+    lin = _f64(q, lut, xe, bits)
+    scale = float(lin.abs().max())
+    if glu:  # rows interleaved (gate_i, up_i): out[i] = fp16(silu(fp16 y[2i])) * fp16(y[2i+1])
+        yh = lin.float().half()
+        gt, up = yh[0::2].float(), yh[1::2]
+        ref = (gt / (1.0 + torch.exp(-gt))).half() * up
+        err = float((y.float() - ref.float()).abs().max()) / float(ref.float().abs().max())
+        assert err <= 4e-3, (variant, bits, err)   # silu(g) * u amplifies the 6e-4 GEMV noise of both factors
+    else:
+        ref = lin.float().half()
+        if res is not None:
+            ref = ref + res
+        err = float((y.float() - ref.float()).abs().max()) / scale
+        assert err <= 2.5e-3, (variant, bits, err)
+
+
+@pytest.mark.parametrize("model,bits,layers,exact", [("tiny", 2, 2, True), ("tiny", 3, 2, True), ("tiny", 4, 2, True),
+                                                      ("llama3-8b", 2, 2, False), ("llama2-7b", 3, 1, False)])
+def test_chain_vs_launch_engine(model, bits, layers, exact):
+    """a chain of GEMV jobs (packets between them) against the per-launch engine: bit-identical when every K <= 8192 (same
+    chunk -> warp map and summation order); for larger K the per-launch kernel runs two chunks per warp (a different fp32
+    association), so the comparison is at the GEMV tolerance"""
     from guidedquant_b200.runtime import ApGemvChain
 
     a = ApGemvChain(model, bits=bits, n_layer=layers, engine="launches")
@@ -29,7 +128,10 @@ def test_chain_bit_identical_to_launch_engine(model, bits, layers):
         torch.cuda.synchronize()
         b.prog.check()
         assert not torch.isnan(yb).any()
-        assert torch.equal(ya.view(torch.int16), yb.view(torch.int16)), (model, bits, float((ya.float() - yb.float()).abs().max()))
+        if exact:
+            assert torch.equal(ya.view(torch.int16), yb.view(torch.int16)), (model, bits, float((ya.float() - yb.float()).abs().max()))
+        else:
+            assert float((ya.float() - yb.float()).abs().max() / ya.float().abs().max()) <= 4e-3
     # repeated launches (the tag advances with the token counter) and the public step() path
     b.capture()
     b.x_in.copy_(x)
@@ -37,8 +139,18 @@ def test_chain_bit_identical_to_launch_engine(model, bits, layers):
         b.step()
     b.stream.synchronize()
     b.prog.check()
-    assert torch.equal(b.y_dev.view(torch.int16), ya.view(torch.int16))
+    assert torch.equal(b.y_dev.view(torch.int16), yb.view(torch.int16))
     assert int(b.prog.epoch.cpu()[0]) >= 7
+
+
+def test_unsupported_shapes_fall_back_to_the_launch_engine():
+    """K > 16384 (Llama-70B w2 on one GPU) does not fit one chunk per consumer warp: the auto engine picks per-launch kernels"""
+    from guidedquant_b200.runtime import ApGemvChain
+
+    ch = ApGemvChain("llama2-70b", bits=2, n_layer=1)
+    assert ch.engine == "launches"
+    with pytest.raises(RuntimeError):
+        ApGemvChain("llama2-70b", bits=2, n_layer=1, engine="persistent").capture()
 
 
 @pytest.mark.parametrize("model,bits", [("tiny128", 2), ("tiny128kv4", 3), ("golden-tiny", 4)])
