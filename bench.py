@@ -364,6 +364,9 @@ def main():
         pg = dist.group.WORLD
 
     def barrier():
+        # drain the device BEFORE the NCCL barrier: a persistent token kernel occupies every SM and waits for its peers'
+        # packets, so an NCCL kernel slipped between two queued token launches on one rank would dead-lock the group
+        torch.cuda.synchronize()
         if world > 1:
             torch.distributed.barrier()
         torch.cuda.synchronize()

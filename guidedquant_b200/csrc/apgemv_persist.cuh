@@ -38,7 +38,8 @@ constexpr uint32_t PK_NB = 32;                   // (full, empty) barrier pairs,
 constexpr uint32_t PK_EMPTY_COUNT = 720720u;     // lcm(1..16): a group of nwk warps arrives with 720720 / nwk each
 constexpr uint32_t PK_SCRATCH_BYTES = 16384;     // per-chunk partial sums of a job / attention scratch
 constexpr uint32_t PK_MAX_STAGE = 32768;
-constexpr long long PK_WATCHDOG_CYCLES = 6000000000ll;  // ~3 s: a wait that long is a bug -> trap instead of hanging the GPU
+constexpr long long PK_WATCHDOG_CYCLES = 40000000000ll;  // ~20 s (ranks of a tensor-parallel group may start seconds apart): a wait
+                                                         // that long is a bug -> trap instead of hanging the GPU
 
 enum : uint32_t { PJ_END = 0, PJ_GEMV = 1, PJ_ATTN = 2, PJ_PACK = 3, PJ_REDUCE = 4 };
 enum : uint32_t { PF_NORM = 1, PF_RESIDUAL = 4, PF_GLU = 8, PF_PUSH = 16 };
@@ -459,14 +460,15 @@ __device__ __noinline__ void pk_pack_job(const uint32_t slot) {
 
 // ------------------------------------------------------------------------------------------------------------
 // attention job: CTA h < H attends for head h with its 16 consumer warps (RoPE + KV append + softmax(q.K^T).V,
-// Attention.forward model.py:206-236; same arithmetic as apd::attn_decode_kernel, decode_kernels.cuh, in blocks of 8
-// cached steps per warp so that the loads in flight fit the 96-register budget of this kernel:
-//   scores: 4 lanes per step, each 32 dims of the K row (4 x 16 B);  P.V: lane = (step mod 4, 16-dim group), 2 passes)
+// Attention.forward model.py:206-236; same arithmetic as apd::attn_decode_kernel, decode_kernels.cuh, in blocks of 4
+// cached steps per warp: lane = (step of the block, 16-dim group) for K and V alike, so a block is one memory round trip
+// of four 16-byte loads per lane and two short FMA runs — long unrolled FMA blocks anywhere in this kernel make ptxas
+// schedule the GEMV row loop conservatively, see pk_gemv_job)
 // ------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void pk_rope4(const __half (&v)[4], const __half (&partner)[4], int lane, const __half (&c)[4],
                                          const __half (&s)[4], __half (&o)[4]) {
     const bool hi = lane >= 16;  // rotate_half: d < 64 -> -x[d+64], d >= 64 -> x[d-64]  (model.py:268-272)
-#pragma unroll 1  // the attention job keeps its loops rolled on purpose: see the note on code shape at pk_gemv_job
+#pragma unroll
     for (int j = 0; j < 4; j++) {
         const __half rot = hi ? partner[j] : __hneg(partner[j]);
         o[j] = __hadd(__hmul(v[j], c[j]), __hmul(rot, s[j]));
@@ -474,7 +476,7 @@ __device__ __forceinline__ void pk_rope4(const __half (&v)[4], const __half (&pa
 }
 
 __device__ __noinline__ void pk_attn_job(const uint32_t slot, const int *pos_ptr) {
-    constexpr int HD = 128, NW = PK_NCW, BS = 8;  // BS cached steps per warp iteration
+    constexpr int HD = 128, NW = PK_NCW, BS = 4;  // BS cached steps per warp iteration
     const PJob &jb = g_sh.jobs[slot];
     const uint32_t H = jb.a0, Hkv = jb.a1, S = jb.a2;
     if (blockIdx.x >= H) return;  // uniform per CTA: the other CTAs move on to the next job
@@ -484,8 +486,7 @@ __device__ __noinline__ void pk_attn_job(const uint32_t slot, const int *pos_ptr
     const uint32_t G = H / Hkv, h = blockIdx.x, kvh = h / G;
     const uint32_t ep = g_sh.tag_base + jb.tag_x, ep_out = g_sh.tag_base + jb.tag_out;
     float *qs = scratch;                                             // [128] roped q (fp32)
-    float(*sc)[BS] = reinterpret_cast<float(*)[BS]>(scratch + HD);   // [NW][8] probabilities of the block in flight
-    float(*wacc)[HD + 4] = reinterpret_cast<float(*)[HD + 4]>(scratch + HD + NW * BS);  // [NW][132]: (m, l, -, -, acc[128])
+    float(*wacc)[HD + 4] = reinterpret_cast<float(*)[HD + 4]>(scratch + HD);  // [NW][132]: (m, l, -, -, acc[128])
     __half *k_cache = static_cast<__half *>(jb.p1), *v_cache = static_cast<__half *>(jb.p2);
     const uint2 *qkv = static_cast<const uint2 *>(jb.x);
     int pos = *static_cast<const volatile int *>(pos_ptr);
@@ -524,85 +525,62 @@ __device__ __noinline__ void pk_attn_job(const uint32_t slot, const int *pos_ptr
 
     const __half *Kb = k_cache + (size_t)kvh * S * HD;
     const __half *Vb = v_cache + (size_t)kvh * S * HD;
-    const int nblk = (pos + BS - 1) / BS;  // blocks of cached steps t < pos
-    const int st = lane >> 2, qd = lane & 3;   // scores: step within the block, 32-dim quarter
-    const int tg = lane >> 3, dg = lane & 7;   // P.V:    step mod 4, 16-dim group
+    const int nblk = (pos + BS - 1) / BS;  // blocks of BS = 4 cached steps t < pos
+    const int tg = lane >> 3, dg = lane & 7;   // lane = (step of the block, 16-dim group) for K and for V alike
     float m = -CUDART_INF_F, l = 0.f, acc[16];
 #pragma unroll
     for (int j = 0; j < 16; j++) acc[j] = 0.f;
+    float qv[16];  // this lane's 16 dims of the roped q
+#pragma unroll
+    for (int j = 0; j < 16; j += 4) {
+        const float4 t = *reinterpret_cast<const float4 *>(qs + 16 * dg + j);
+        qv[j] = t.x, qv[j + 1] = t.y, qv[j + 2] = t.z, qv[j + 3] = t.w;
+    }
 #pragma unroll 1
     for (int b = w; b < nblk; b += NW) {
-        const int tb = b * BS, nt = min(BS, pos - tb);
-        // ---- all loads of the block first (one memory round trip): this lane's quarter K row and its two V pieces
-        uint4 kv[4], vv[2][2];
-        if (st < nt) {
-            const uint4 *kr4 = reinterpret_cast<const uint4 *>(Kb + (size_t)(tb + st) * HD + 32 * qd);
-#pragma unroll
-            for (int i = 0; i < 4; i++) kv[i] = __ldcg(kr4 + i);
+        const int t = b * BS + tg;
+        const bool ok = t < pos;
+        // ---- the block's loads first (one memory round trip): 32 bytes of the K row and of the V row of this lane's step
+        uint4 k0 = make_uint4(0, 0, 0, 0), k1 = k0, v0 = k0, v1 = k0;
+        if (ok) {
+            const uint4 *kr4 = reinterpret_cast<const uint4 *>(Kb + (size_t)t * HD + 16 * dg);
+            const uint4 *vr4 = reinterpret_cast<const uint4 *>(Vb + (size_t)t * HD + 16 * dg);
+            k0 = __ldcg(kr4), k1 = __ldcg(kr4 + 1), v0 = __ldcg(vr4), v1 = __ldcg(vr4 + 1);
         }
-#pragma unroll
-        for (int u = 0; u < 2; u++) {
-            const int tt = 4 * u + tg;
-            vv[u][0] = vv[u][1] = make_uint4(0, 0, 0, 0);
-            if (tt < nt) {
-                const uint4 *vr = reinterpret_cast<const uint4 *>(Vb + (size_t)(tb + tt) * HD + 16 * dg);
-                vv[u][0] = __ldcg(vr), vv[u][1] = __ldcg(vr + 1);
-            }
-        }
-        // ---- scores
+        // ---- score of the step: 16 dims per lane, summed over the 8 lanes of the step
+        const uint32_t kw[8] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w};
         float a0 = 0.f, a1 = 0.f;
-        if (st < nt) {
-#pragma unroll 1  // kept rolled on purpose: see the note on code shape at pk_gemv_job
-            for (int i = 0; i < 4; i++) {
-                const float4 qa = *reinterpret_cast<const float4 *>(qs + 32 * qd + 8 * i);
-                const float4 qb = *reinterpret_cast<const float4 *>(qs + 32 * qd + 8 * i + 4);
-                const float2 k0 = __half22float2(*reinterpret_cast<const __half2 *>(&kv[i].x));
-                const float2 k1 = __half22float2(*reinterpret_cast<const __half2 *>(&kv[i].y));
-                const float2 k2 = __half22float2(*reinterpret_cast<const __half2 *>(&kv[i].z));
-                const float2 k3 = __half22float2(*reinterpret_cast<const __half2 *>(&kv[i].w));
-                a0 = fmaf(qa.x, k0.x, a0), a1 = fmaf(qa.y, k0.y, a1);
-                a0 = fmaf(qa.z, k1.x, a0), a1 = fmaf(qa.w, k1.y, a1);
-                a0 = fmaf(qb.x, k2.x, a0), a1 = fmaf(qb.y, k2.y, a1);
-                a0 = fmaf(qb.z, k3.x, a0), a1 = fmaf(qb.w, k3.y, a1);
-            }
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const float2 f = __half22float2(*reinterpret_cast<const __half2 *>(&kw[j]));
+            a0 = fmaf(qv[2 * j], f.x, a0), a1 = fmaf(qv[2 * j + 1], f.y, a1);
         }
         float s = a0 + a1;
         s += __shfl_xor_sync(0xffffffffu, s, 1);
         s += __shfl_xor_sync(0xffffffffu, s, 2);
-        s = (st < nt) ? s * scale : -CUDART_INF_F;
-        // ---- online softmax update (every lane of a step's quad holds the same score)
-        float bm = s;
-#pragma unroll
-        for (int o = 16; o >= 4; o >>= 1) bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, o));
+        s += __shfl_xor_sync(0xffffffffu, s, 4);
+        s = ok ? s * scale : -CUDART_INF_F;
+        // ---- online softmax update over the block's 4 steps (every lane of a step holds its score)
+        float bm = fmaxf(s, __shfl_xor_sync(0xffffffffu, s, 8));
+        bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, 16));
         const float mn = fmaxf(m, bm);
         const float corr = __expf(m - mn);
-        const float pe = (st < nt) ? __expf(s - mn) : 0.f;
-        float bl = pe;
-#pragma unroll
-        for (int o = 16; o >= 4; o >>= 1) bl += __shfl_xor_sync(0xffffffffu, bl, o);
+        const float pe = ok ? __expf(s - mn) : 0.f;
+        float bl = pe + __shfl_xor_sync(0xffffffffu, pe, 8);
+        bl += __shfl_xor_sync(0xffffffffu, bl, 16);
         l = l * corr + bl;
         m = mn;
-        __syncwarp();
-        if (qd == 0) sc[w][st] = pe;
-        __syncwarp();
-        // ---- acc = acc * corr + P.V of the block
+        // ---- acc = acc * corr + p * V (this lane: its step, its 16 dims; the 4 steps are summed after the loop)
+        const uint32_t vw[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
 #pragma unroll
-        for (int j = 0; j < 16; j++) acc[j] *= corr;
-#pragma unroll 1
-        for (int u = 0; u < 2; u++) {
-            const int tt = 4 * u + tg;
-            const float pw = (tt < nt) ? sc[w][tt] : 0.f;
-            const uint32_t wv[8] = {vv[u][0].x, vv[u][0].y, vv[u][0].z, vv[u][0].w, vv[u][1].x, vv[u][1].y, vv[u][1].z, vv[u][1].w};
-#pragma unroll
-            for (int j = 0; j < 8; j++) {
-                const float2 f = __half22float2(*reinterpret_cast<const __half2 *>(&wv[j]));
-                acc[2 * j] = fmaf(pw, f.x, acc[2 * j]);
-                acc[2 * j + 1] = fmaf(pw, f.y, acc[2 * j + 1]);
-            }
+        for (int j = 0; j < 8; j++) {
+            const float2 f = __half22float2(*reinterpret_cast<const __half2 *>(&vw[j]));
+            acc[2 * j] = fmaf(pe, f.x, acc[2 * j] * corr);
+            acc[2 * j + 1] = fmaf(pe, f.y, acc[2 * j + 1] * corr);
         }
     }
     // sum the four step groups of the warp; lanes with tg == 0 publish the warp's state
-#pragma unroll 4
+#pragma unroll
     for (int j = 0; j < 16; j++) {
         acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 8);
         acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 16);
@@ -623,7 +601,7 @@ __device__ __noinline__ void pk_attn_job(const uint32_t slot, const int *pos_ptr
         for (int o = 16; o >= 1; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
         const float s_cur = d * scale;
         float M = s_cur;
-#pragma unroll 1
+#pragma unroll
         for (int i = 0; i < NW; i++) M = fmaxf(M, wacc[i][0]);
         float Lsum = 0.f, a4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
@@ -765,7 +743,7 @@ __global__ void __launch_bounds__(PK_THREADS, 1) decode_persistent_kernel(const 
             while (!*static_cast<volatile uint32_t *>(&g_sh.p_done)) {
                 pk_produce();
                 __nanosleep(128);
-                if (clock64() - t0 > 40 * PK_WATCHDOG_CYCLES) pk_die(p.err, 4u);
+                if (clock64() - t0 > 8 * PK_WATCHDOG_CYCLES) pk_die(p.err, 4u);
             }
         }
     } else {

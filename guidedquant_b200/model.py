@@ -22,7 +22,7 @@ import math
 import torch
 
 from . import _lib
-from .runtime import MODEL_CONFIGS, gemv_algo_bytes, linear_shapes, persistent_supported
+from .runtime import MODEL_CONFIGS, PERSISTENT_MIN_WORLD, gemv_algo_bytes, linear_shapes, persistent_supported
 
 ROPE_BASE = {"llama3-8b": 500000.0, "llama3-70b": 500000.0, "llama2-7b": 10000.0, "llama2-70b": 10000.0, "tiny": 500000.0,
              "golden-tiny": 500000.0, "tiny128": 500000.0, "tiny128kv4": 500000.0}
@@ -37,10 +37,11 @@ class APTransformer:
                  world_size: int = 1, rank: int = 0, process_group=None, glu_epilogue: bool | None = None,
                  engine: str | None = None):
         self.cfg = dict(MODEL_CONFIGS[model])
-        # "persistent" (default under tensor parallelism): embedding + all blocks of a token are ONE cooperative launch of
+        # "persistent" (default from 4 GPUs on): embedding + all blocks of a token are ONE cooperative launch of
         # the persistent token kernel (persist.py / csrc/apgemv_persist.cuh), then lm_head + sampling;
         # "launches" (default on one GPU, measured faster there): one PDL launch per op
-        self.engine = engine or ("persistent" if world_size > 1 and persistent_supported(self.cfg, bits, world_size) else "launches")
+        self.engine = engine or ("persistent" if world_size >= PERSISTENT_MIN_WORLD and persistent_supported(self.cfg, bits, world_size)
+                                 else "launches")
         assert self.engine in ("launches", "persistent"), f"unknown decode engine {engine!r}"
         self.prog = None
         if n_layer is not None:
@@ -406,6 +407,9 @@ class APTransformer:
             s.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(s):
                 saved = (self.token.clone(), self.pos.clone())
+                if self.world > 1:  # ranks finish loading at different times: line them up before the first exchange
+                    s.synchronize()
+                    torch.distributed.barrier(self.pg)
                 self.decode_step()  # warm-up (function attributes, lazy init); its side effects are undone below
                 s.synchronize()
                 if self.prog is not None:

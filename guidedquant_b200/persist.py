@@ -52,7 +52,8 @@ class PersistentProgram:
         self.keep: list = []            # tensors the job table points to
         self.jobs_dev: torch.Tensor | None = None
         self.epoch = torch.zeros(2, dtype=torch.int32, device=self.device)   # token counter (packets carry epoch*n_jobs + job)
-        self.err = torch.zeros(1, dtype=torch.int32, device=self.device)     # watchdog word
+        # watchdog word in pinned HOST memory (device-mapped): still readable after a device-side trap killed the context
+        self.err = torch.zeros(1, dtype=torch.int32).pin_memory()
         self.done = torch.zeros(1, dtype=torch.int32, device=self.device)
         self.prof: torch.Tensor | None = None   # enable_profile(): int64 [SMs, n_jobs, 4] clock stamps of the last launch
 
@@ -168,7 +169,7 @@ class PersistentProgram:
 
     def check(self):
         """synchronising: raise if a device-side watchdog fired (a wait that never completed)"""
-        e = int(self.err.cpu()[0]) & 0xFFFFFFFF
+        e = int(self.err[0]) & 0xFFFFFFFF
         if e:
             raise RuntimeError(f"persistent kernel watchdog: code {e & 0xff} (1/2 packet wait, 3 weight stage, 4 ring slot, "
                                f"5 bad job, 6 smem alignment), cta {(e >> 8) & 0xfff}, thread {e >> 20}")

@@ -44,6 +44,11 @@ def linear_shapes(cfg: dict) -> dict:
     }
 
 
+# measured on B200 (Llama-3-8B 2-bit, profiles/r2_engines_by_world.txt): per-launch kernels win on 1 GPU (812 vs 619 tok/s), tie on 2
+# (863 vs 856), the persistent token kernel wins from 4 GPUs on (981 vs 895), where the per-GPU Linears are small
+PERSISTENT_MIN_WORLD = 4
+
+
 def persistent_supported(cfg: dict, bits: int, world: int = 1) -> bool:
     """the persistent token kernel takes K <= 16384 per GEMV job (one 1024-chunk per consumer warp) with 4 rows of all planes
     within a 32 KB stage; Llama-70B's w2 (K = 28672) on ONE GPU does not fit and runs on the per-launch engine"""
@@ -81,7 +86,7 @@ class ApGemvChain:
         # default: per-launch kernels on one GPU (measured faster there: the hand-over between two Linears costs about the
         # same either way and the per-launch kernel keeps 18 warps per SM busy); the persistent kernel under
         # tensor parallelism, where the per-GPU Linears are small and the launch count is what bounds a token
-        ok = world_size > 1 and collective == "push" and persistent_supported(self.cfg, bits, world_size)
+        ok = world_size >= PERSISTENT_MIN_WORLD and collective == "push" and persistent_supported(self.cfg, bits, world_size)
         self.engine = engine or ("persistent" if ok else "launches")
         assert self.engine in ("launches", "persistent"), f"unknown engine {engine!r}"
         self.prog = None
@@ -246,6 +251,9 @@ class ApGemvChain:
             with torch.cuda.device(self.device):
                 if self.prog is None:
                     self._build_program()
+                if self.world > 1:  # ranks finish building at different times: line them up before the first exchange
+                    torch.cuda.synchronize()
+                    torch.distributed.barrier(self.pg)
                 with torch.cuda.stream(self.stream):
                     self.prog.launch()  # warm-up (function attributes)
                 self.stream.synchronize()

@@ -53,7 +53,8 @@ def _persist_gemv(q, lut, x, bits, norm_w=None, residual=None, glu=False):
 
 @pytest.mark.parametrize("bits", [2, 3, 4])
 @pytest.mark.parametrize("N,K", [(4096, 4096), (6144, 4096), (28672, 4096), (4096, 14336), (10240, 8192), (8192, 8192),
-                                 (8192, 3584), (4096, 11008), (100, 1024), (2, 128), (1026, 2176)])
+                                 (8192, 3584), (4096, 11008), (100, 1024), (2, 128), (1026, 2176),
+                                 (4096, 1024), (4096, 3584), (1536, 4096), (7168, 4096), (4096, 512), (4096, 1792), (768, 4096)])  # TP4 / TP8 shards
 def test_persistent_gemv_job_vs_f64_and_launch_kernel(N, K, bits):
     """a single GEMV job of the persistent kernel at the benchmark shapes (and ragged ones): within the stated tolerance of the
     fp64 truth, and BIT-IDENTICAL to the per-launch kernel whenever that one also runs one K chunk per warp (K <= 8192)."""
