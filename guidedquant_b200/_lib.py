@@ -15,9 +15,9 @@ _ROOT = os.path.dirname(_PKG)
 _CSRC = os.path.join(_PKG, "csrc")
 _LIBDIR = os.path.join(_PKG, "lib")
 LIB_PATH = os.path.join(_LIBDIR, "libapgemv_b200.so")
-_SOURCES = ["apgemv_capi.cu", "decode_capi.cu", "persist_capi.cu"]
+_SOURCES = ["apgemv_capi.cu", "decode_capi.cu", "persist_capi.cu", "prefill_capi.cu"]
 _HEADERS = ["apgemv_common.cuh", "apgemv_fast.cuh", "apgemv_generic.cuh", "apgemv_wide.cuh", "decode_kernels.cuh",
-            "apgemv_persist.cuh"]
+            "apgemv_persist.cuh", "prefill_tc.cuh"]
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-lineinfo", "-shared", "-Xcompiler", "-fPIC", "-t", "4",
@@ -30,7 +30,7 @@ EXPORTS = (
     "apd_embed", "apd_attn_decode", "apd_lm_head", "apd_argmax_advance", "apd_argmax_advance_tp",
     "apd_sample_topk_advance", "apg_plan_fast",
     "apg_persist_job_bytes", "apg_persist_smem", "apg_persist_job_gemv", "apg_persist_job_attn", "apg_persist_job_pack",
-    "apg_persist_job_reduce", "apg_persist_launch",
+    "apg_persist_job_reduce", "apg_persist_launch", "apg_prefill_plan", "apg_prefill_gemm",
 )
 
 
@@ -121,6 +121,10 @@ def lib() -> ctypes.CDLL:
     L.apg_gemv_ex.argtypes = [vp, vp, vp, vp, vp, u32, u32, u32, i32, u32, i32, vp]
     L.apg_dequant.restype = i32
     L.apg_dequant.argtypes = [vp, vp, vp, u32, u32, i32, vp]
+    L.apg_prefill_plan.restype = i32
+    L.apg_prefill_plan.argtypes = [u32, u32, u32, i32, i32, ctypes.POINTER(u32), ctypes.POINTER(ctypes.c_uint64)]
+    L.apg_prefill_gemm.restype = i32
+    L.apg_prefill_gemm.argtypes = [vp, vp, vp, vp, u32, u32, u32, i32, vp, ctypes.c_uint64, vp]
     L.apg_gemv_fused.restype = i32
     L.apg_gemv_fused.argtypes = [vp, vp, vp, vp, vp, u32, u32, i32, vp, ctypes.c_float, i32, vp, u32, vp]
     f32 = ctypes.c_float
@@ -173,7 +177,7 @@ def check(status: int, what: str) -> None:
         raise RuntimeError(f"{what}: {msg}{extra}")
 
 
-APG_VERSION = 200  # include/apgemv_b200.h: major*100 + minor
+APG_VERSION = 201  # include/apgemv_b200.h: major*100 + minor
 APG_FLAG_REF_ORDER = 0x1
 APG_FLAG_GENERIC = 0x2
 APG_FLAG_PDL = 0x4

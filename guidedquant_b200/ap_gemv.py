@@ -12,11 +12,13 @@ any_precision/modules/AnyPrecisionLinear.py run unmodified on top of it.
 """
 from __future__ import annotations
 
+import ctypes
+
 import torch
 
 from . import _lib
 
-__all__ = ["anyprec_gemv", "anyprec_dequant", "anyprec_gemv_ex"]
+__all__ = ["anyprec_gemv", "anyprec_dequant", "anyprec_gemv_ex", "anyprec_prefill_gemm", "prefill_supported"]
 
 
 def _req(cond: bool, msg: str) -> None:
@@ -98,6 +100,52 @@ def anyprec_dequant(qweight: torch.Tensor, lut: torch.Tensor, bitwidth: int) -> 
                                     _stream(qweight.device))
     _lib.check(st, "anyprec_dequant")
     return weight
+
+
+def prefill_supported(qweight: torch.Tensor, bitwidth: int) -> bool:
+    """shapes the fused tensor-core prefill kernel takes (include/apgemv_b200.h, apg_prefill_gemm)"""
+    return 2 <= bitwidth <= 4 and (qweight.size(2) * 32) % 256 == 0
+
+
+_workspaces: dict = {}  # (device index, stream) -> fp32 scratch of the split-K partial sums, grown on demand
+
+
+def anyprec_prefill_gemm(input: torch.Tensor, qweight: torch.Tensor, lut: torch.Tensor, bitwidth: int) -> torch.Tensor:
+    """x [..., K] fp16 -> x @ dequant(qweight, lut).T [..., N] fp16 in ONE kernel (csrc/prefill_tc.cuh): the fused form of
+    the reference's prefill branch `anyprec_dequant` + `torch.matmul` (inference/ap_gemv/APLinear.py:35-38)."""
+    _req(input.is_cuda and qweight.is_cuda and lut.is_cuda and input.device == qweight.device == lut.device,
+         "input, qweight and lut must be on the same GPU.")
+    _req(input.dtype == torch.float16, "input must be float16.")
+    _req(qweight.dtype == torch.int32 and qweight.dim() == 3 and qweight.is_contiguous(),
+         "qweight tensor must be a contiguous int tensor of shape (bitwidth, output_feat, input_feat / 32).")
+    _req(qweight.size(0) >= bitwidth, "qweight has fewer bit-planes than bitwidth.")
+    N, K = qweight.size(1), qweight.size(2) * 32
+    _req(input.shape[-1] == K, f"input feature size {input.shape[-1]} does not match the weight ({K}).")
+    _req(lut.dtype == torch.float16 and lut.is_contiguous() and tuple(lut.shape) == (N, 1 << bitwidth),
+         f"lut tensor must be a contiguous float16 tensor of shape ({N}, {1 << bitwidth}).")
+    _req(prefill_supported(qweight, bitwidth), "the fused prefill kernel needs bits in 2..4 and K % 256 == 0.")
+    x2 = input.reshape(-1, K)
+    if not x2.is_contiguous():
+        x2 = x2.contiguous()
+    T = x2.shape[0]
+    out = torch.empty((T, N), dtype=torch.float16, device=input.device)
+    L = _lib.lib()
+    with torch.cuda.device(input.device):
+        stream = _stream(input.device)
+        plan = (ctypes.c_uint32 * 8)()
+        need = ctypes.c_uint64(0)
+        sms = torch.cuda.get_device_properties(input.device).multi_processor_count
+        _lib.check(L.apg_prefill_plan(T, N, K, bitwidth, sms, plan, ctypes.byref(need)), "apg_prefill_plan")
+        ws = None
+        if need.value:
+            key = (input.device.index, stream)
+            ws = _workspaces.get(key)
+            if ws is None or ws.numel() * 4 < need.value:
+                ws = _workspaces[key] = torch.empty((need.value + 3) // 4, dtype=torch.float32, device=input.device)
+        st = L.apg_prefill_gemm(x2.data_ptr(), out.data_ptr(), qweight.data_ptr(), lut.data_ptr(), T, N, K, bitwidth,
+                                ws.data_ptr() if ws is not None else None, need.value, stream)
+    _lib.check(st, "anyprec_prefill_gemm")
+    return out.reshape(*input.shape[:-1], N)
 
 
 def lutgemm_gemv(*args, **kwargs):

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define APG_VERSION 200 /* major*100 + minor */
+#define APG_VERSION 201 /* major*100 + minor */
 
 enum apg_status {
     APG_OK = 0,
@@ -138,6 +138,21 @@ int apg_plan_fast(uint32_t N, uint32_t K, int bits, int ctas_per_sm, int sms, ui
  */
 int apg_dequant(const void *qweight, const void *lut, void *w_out,
                 uint32_t N, uint32_t K, int bits, void *stream);
+
+/*
+ * Prefill: replaces the reference's dequantise-then-matmul branch for more than 8 tokens
+ *   (inference/ap_gemv/APLinear.py:35-38, any_precision/modules/AnyPrecisionLinear.py forward: anyprec_dequant + torch.matmul).
+ * out[t, n] = sum_k x[t, k] * lut[n, idx[n, k]], x fp16 [T, K] row-major, out fp16 [T, N], fp32 accumulation, one rounding.
+ * ONE kernel: the packed weights are dequantised straight into the shared-memory operand tiles of tcgen05.mma (the fp16 [N, K]
+ * weight never exists in HBM), token tiles arrive by TMA, accumulators live in TMEM (csrc/prefill_tc.cuh).
+ * Supported: bits 2..4, K % 256 == 0, x / qweight / lut 16-byte aligned; anything else returns APG_ERR_UNSUPPORTED and the
+ * caller keeps the apg_dequant + library-GEMM route.  Small T*N splits K over CTAs and needs `workspace`
+ * (apg_prefill_plan reports the bytes; without it the call still succeeds, with one CTA per tile walking the whole K).
+ * plan[8] = {tokens per CTA, token tiles, row tiles, K splits, ring stages, dynamic smem bytes, TMEM columns, K/256}.
+ */
+int apg_prefill_plan(uint32_t T, uint32_t N, uint32_t K, int bits, int sms, uint32_t plan[8], uint64_t *workspace_bytes);
+int apg_prefill_gemm(const void *x, void *out, const void *qweight, const void *lut, uint32_t T, uint32_t N, uint32_t K, int bits,
+                     void *workspace, uint64_t workspace_bytes, void *stream);
 
 /* fp32 [n] -> fp16 [n] round-to-nearest-even; the epilogue of the K-sharded path after the fp32 all-reduce. */
 int apg_round_f32_to_f16(const float *in, void *out, uint32_t n, void *stream);
