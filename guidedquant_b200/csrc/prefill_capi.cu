@@ -62,14 +62,15 @@ int make_plan(uint32_t T, uint32_t N, uint32_t K, int bits, int sms, int allow_s
     pl->splits = splits;
     pl->workspace_bytes = splits > 1 ? (uint64_t)splits * T * N * sizeof(float) : 0;
     const uint32_t base = stage_base(bits);
-    const uint32_t per_stage = A_TILE + t_tile * (BK * 2);
+    const uint32_t per_stage = t_tile * (BK * 2);  // token tile in shared memory; the weight tile of a stage lives in TMEM
     uint32_t stages = (SMEM_LIMIT - 1024u - base) / per_stage;
     if (stages > MAX_STAGES) stages = MAX_STAGES;
+    if (stages > (512u - t_tile) / A_COLS) stages = (512u - t_tile) / A_COLS;
     if (stages < 2) return APG_ERR_UNSUPPORTED;
     pl->stages = stages;
     pl->smem_bytes = base + stages * per_stage;  // dynamic shared memory starts at (or near) shared address 0
     uint32_t cols = 32;
-    while (cols < t_tile) cols *= 2;
+    while (cols < t_tile + stages * A_COLS) cols *= 2;
     pl->tmem_cols = cols;
     return APG_OK;
 }

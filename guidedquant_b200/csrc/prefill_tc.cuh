@@ -9,13 +9,15 @@
 //   * "swap-AB": the 128 weight rows are the M side of tcgen05.mma (cta_group::1, kind::f16, M = 128), the tokens are the
 //     N side (N = T_TILE, 32..256), so a decode-sized token tile still uses the full 128-lane datapath.  The fp32
 //     accumulator tile [128 lanes x T_TILE columns] lives in TMEM.
-//   * A operand = dequantised weights, never in HBM: 8 warps (two threads per weight row) read the packed bit-plane words
-//     of their row straight from global memory (16 B per plane per 256 k), turn them into table indices with the same
-//     LOP3 networks as the GEMV kernels, look the fp16 pairs up in bank-striped shared-memory tables (one LDS = two
-//     weights, conflict-free: entry-major, lane-minor) and store 16-byte pieces into the 128-byte-swizzled K-major tile the
-//     MMA reads (st.shared.v4 + fence.proxy.async).  The packed layout makes this cheap: byte c of word t of a chunk holds
-//     8 CONSECUTIVE k (k = i*1024 + c*8*eff + 8t + e, pack.py:58-75), so a K block of 64 consecutive k is "byte c of 8
-//     consecutive words" and the token tile needs no permutation at all.
+//   * A operand = dequantised weights, never in HBM and never in shared memory: 8 warps (two threads per weight row) read
+//     the packed bit-plane words of their row straight from global memory (16 B per plane per 256 k), turn them into table
+//     indices with the same LOP3 networks as the GEMV kernels, look the fp16 pairs up in bank-striped shared-memory tables
+//     (one LDS = two weights, conflict-free: entry-major, lane-minor) and write them with tcgen05.st into a ring of A tiles
+//     IN TMEM (tcgen05.mma with the A operand in tensor memory: lane = weight row, one 32-bit column = two consecutive k —
+//     exactly the thread-per-row order the dequantiser produces, so there is no swizzle, no st.shared, no proxy fence, and
+//     the MMA reads only the token tile from shared memory).  The packed layout makes this cheap: byte c of word t of a
+//     chunk holds 8 CONSECUTIVE k (k = i*1024 + c*8*eff + 8t + e, pack.py:58-75), so a K block of 64 consecutive k is
+//     "byte c of 8 consecutive words" and the token tile needs no permutation at all.
 //   * B operand = the token tile [T_TILE x 64] of X, loaded by TMA (cp.async.bulk.tensor.2d, SWIZZLE_128B) by one thread;
 //     rows past T are zero-filled by the TMA unit.
 //   * One elected thread issues the MMAs (4 x K=16 per stage) and releases stages with tcgen05.commit; a ring of
@@ -40,7 +42,7 @@ constexpr int THREADS = (DQ_WARPS + 2) * 32;
 constexpr int MAX_STAGES = 8;
 constexpr uint32_t CTRL_BYTES = 256;          // barriers + TMEM base, at the very start of dynamic shared memory
 constexpr uint32_t TBL_ABS = 2048;            // ABSOLUTE shared address of the lookup tables: an LDS immediate
-constexpr uint32_t A_TILE = ROWS * BK * 2;    // 16 KB
+constexpr uint32_t A_COLS = BK / 2;            // TMEM columns of one A stage (two fp16 per 32-bit column)
 constexpr uint32_t SMEM_LIMIT = 227u * 1024u;
 constexpr long long WATCHDOG_CYCLES = 6000000000ll;  // ~3 s: a wait that long is a bug; trap instead of hanging the GPU
 
@@ -62,7 +64,7 @@ struct Cfg<4> {
 template <int BITS>
 struct Lay {
     static constexpr uint32_t TBL_BYTES = 2u * (1u << Cfg<BITS>::ENTRY_BITS) * 256u;
-    static constexpr uint32_t STAGE_BASE = (TBL_ABS + TBL_BYTES + 1023u) & ~1023u;  // absolute shared address of A tile 0
+    static constexpr uint32_t STAGE_BASE = (TBL_ABS + TBL_BYTES + 1023u) & ~1023u;  // absolute shared address of token tile 0
 };
 
 struct Params {
@@ -75,7 +77,7 @@ struct Params {
     uint32_t stages;     // ring depth
     uint32_t splits;     // K split over gridDim.z
     uint32_t sb_total;   // K / 256 "super blocks" (8 words per row and plane = 4 stages)
-    uint32_t tmem_cols;  // power of two >= t_tile, >= 32
+    uint32_t tmem_cols;  // power of two >= t_tile + stages * A_COLS: accumulator columns [0, t_tile), then the A ring
     uint32_t idesc;      // tcgen05 instruction descriptor
 };
 
@@ -129,14 +131,23 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr) {
     return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024u >> 4) << 32) | ((uint64_t)1 << 46) |
            ((uint64_t)2 << 61);
 }
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+// D[tmem] (+)= A[tmem] * B[smem]: A = 128 lanes x 8 columns (16 fp16 of k per row), B described by `db`
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-        "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(db), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// 16 consecutive 32-bit columns of this thread's TMEM lane (warp-collective; taddr = lane-quadrant base | column)
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint4 &a, const uint4 &b, const uint4 &c, const uint4 &d) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+                 "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w), "r"(c.x), "r"(c.y), "r"(c.z), "r"(c.w),
+                 "r"(d.x), "r"(d.y), "r"(d.z), "r"(d.w)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -148,9 +159,6 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
         : "r"(taddr)
         : "memory");
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void sts_v4(uint32_t addr, const uint4 &v) {
-    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 __device__ __forceinline__ void sts_b32(uint32_t addr, uint32_t v) {
     asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
@@ -178,7 +186,7 @@ __device__ __forceinline__ uint32_t comp(const uint4 &v, int i) { return i == 0 
 // ------------------------------------------------------------------------------------------------ index networks
 // Net<BITS>::run turns one word per plane (32 weights of one row) into NREG registers of table-index bytes; byte B of those
 // registers belongs to byte B of the packed word, i.e. to c = 3 - B (bit 31 - (8c+e)).  Net<BITS>::gather<B> looks up
-// the 8 weights e = 0..7 of that byte: four half2 (even e in the low half) = one 16-byte piece of an A-tile row.
+// the 8 weights e = 0..7 of that byte: four half2 (even e in the low half) = four consecutive A columns of the row.
 template <int BITS>
 struct Net;
 
@@ -289,8 +297,7 @@ __global__ void __launch_bounds__(THREADS, 1) prefill_tc_kernel(const __grid_con
     const uint32_t s0 = smem_u32(ptc_smem);
     // control block: full[MAX_STAGES], empty[MAX_STAGES], accum, tmem base
     const uint32_t bar_full = s0, bar_empty = s0 + 8 * MAX_STAGES, bar_accum = s0 + 16 * MAX_STAGES, tmem_slot = bar_accum + 8;
-    const uint32_t a_base = Lay<BITS>::STAGE_BASE;
-    const uint32_t b_base = a_base + p.stages * A_TILE;
+    const uint32_t b_base = Lay<BITS>::STAGE_BASE;
     const uint32_t b_tile = p.t_tile * (BK * 2);
     uint32_t dyn_size;
     asm("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn_size));
@@ -338,10 +345,9 @@ __global__ void __launch_bounds__(THREADS, 1) prefill_tc_kernel(const __grid_con
         const uint32_t wpr4 = p.K >> 7;  // uint4 per row and plane
         const uint4 *wrow = reinterpret_cast<const uint4 *>(p.W) + (size_t)grow * wpr4 + h;
         const size_t plane4 = (size_t)p.N * wpr4;
-        const uint32_t row_off = (row >> 3) * 1024 + (row & 7) * 128;
-        uint32_t piece[4];
-#pragma unroll
-        for (int tt = 0; tt < 4; tt++) piece[tt] = row_off + (((4 * h + tt) ^ (row & 7)) << 4);
+        // A ring in TMEM: stage s = columns t_tile + s*A_COLS .. +31 of all 128 lanes; this warp owns lanes 32*(warp&3)..+31
+        // and, of a stage, the 16 columns of its 4 words
+        const uint32_t a_tmem = tmem_base + (((warp & 3) * 32) << 16) + p.t_tile + h * 16;
 
         uint4 cur[BITS], nxt[BITS];
 #pragma unroll
@@ -361,18 +367,19 @@ __global__ void __launch_bounds__(THREADS, 1) prefill_tc_kernel(const __grid_con
             }
 #pragma unroll
             for (int c = 0; c < 4; c++) {
-                mb_wait(bar_empty + 8 * s, ph ^ 1);
-                const uint32_t a_s = a_base + s * A_TILE;
+                uint4 v[4];
 #pragma unroll
                 for (int tt = 0; tt < 4; tt++) {
-                    uint4 v;
-                    if (c == 0) v = Net<BITS>::template gather<3>(o[tt], lb);
-                    if (c == 1) v = Net<BITS>::template gather<2>(o[tt], lb);
-                    if (c == 2) v = Net<BITS>::template gather<1>(o[tt], lb);
-                    if (c == 3) v = Net<BITS>::template gather<0>(o[tt], lb);
-                    sts_v4(a_s + piece[tt], v);
+                    if (c == 0) v[tt] = Net<BITS>::template gather<3>(o[tt], lb);
+                    if (c == 1) v[tt] = Net<BITS>::template gather<2>(o[tt], lb);
+                    if (c == 2) v[tt] = Net<BITS>::template gather<1>(o[tt], lb);
+                    if (c == 3) v[tt] = Net<BITS>::template gather<0>(o[tt], lb);
                 }
-                fence_proxy_async();
+                mb_wait(bar_empty + 8 * s, ph ^ 1);  // the MMAs that read this A stage (and token tile) have completed
+                tc_fence_after();
+                tmem_st16(a_tmem + s * A_COLS, v[0], v[1], v[2], v[3]);
+                tmem_wait_st();
+                tc_fence_before();
                 mb_arrive(bar_full + 8 * s);
                 if (++s == p.stages) s = 0, ph ^= 1;
             }
@@ -428,10 +435,11 @@ __global__ void __launch_bounds__(THREADS, 1) prefill_tc_kernel(const __grid_con
             for (uint32_t it = 0; it < n_it; it++) {
                 mb_wait(bar_full + 8 * s, ph);
                 tc_fence_after();
-                const uint64_t da = smem_desc(a_base + s * A_TILE), db = smem_desc(b_base + s * b_tile);
+                const uint64_t db = smem_desc(b_base + s * b_tile);
+                const uint32_t ta = tmem_base + p.t_tile + s * A_COLS;
 #pragma unroll
                 for (uint32_t kk = 0; kk < BK / 16; kk++) {
-                    umma_f16(tmem_base, da + 2 * kk, db + 2 * kk, p.idesc, acc);
+                    umma_f16_ts(tmem_base, ta + 8 * kk, db + 2 * kk, p.idesc, acc);
                     acc = 1;
                 }
                 umma_commit(bar_empty + 8 * s);

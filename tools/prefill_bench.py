@@ -12,17 +12,25 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from guidedquant_b200 import ap_gemv  # noqa: E402
 
 
-def timed(fn, iters, warm=3):
-    for _ in range(warm):
+def timed(fn, iters, calls, warm=2):
+    """median us per call of `fn`; `calls` consecutive calls (rotating weight copies) are captured into ONE CUDA graph so
+    that the host-side cost of a call (allocation, plan, tensor-map encode: tens of us) is not what is measured"""
+    for _ in range(warm * calls):
         fn()
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(calls):
+            fn()
+    g.replay()
     torch.cuda.synchronize()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(iters + 1)]
     ev[0].record()
     for i in range(iters):
-        fn()
+        g.replay()
         ev[i + 1].record()
     torch.cuda.synchronize()
-    ts = sorted(ev[i].elapsed_time(ev[i + 1]) * 1e3 for i in range(iters))
+    ts = sorted(ev[i].elapsed_time(ev[i + 1]) * 1e3 / calls for i in range(iters))
     return ts[len(ts) // 2]
 
 
@@ -61,7 +69,7 @@ def main():
                 y = ap_gemv.anyprec_prefill_gemm(x, qs[0], lut, bits)
                 truth = x.double() @ W.double().T
                 err = float((y.double() - truth).abs().max() / truth.abs().max())
-                t_f, t_r, t_g = timed(fused, a.iters), timed(ref, a.iters), timed(gemm_only, a.iters)
+                t_f, t_r, t_g = timed(fused, a.iters, ncopy), timed(ref, a.iters, ncopy), timed(gemm_only, a.iters, ncopy)
                 flops = 2.0 * T * N * K
                 print(json.dumps({"N": N, "K": K, "bits": bits, "T": T, "fused_us": round(t_f, 2), "dequant_matmul_us": round(t_r, 2),
                                   "matmul_only_us": round(t_g, 2), "speedup": round(t_r / t_f, 3), "fused_tflops": round(flops / t_f / 1e6, 1),
