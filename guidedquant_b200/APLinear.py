@@ -38,14 +38,14 @@ class APLinear(nn.Module):
         # prefill / seq > 1 (APLinear.py:35-38 does dequant -> fp16 matmul).  Up to 8 tokens go through the batched LUT
         # GEMV instead (the kernel's M dimension, gemv.cu:41): the packed weights are read once and no fp16 copy of the
         # matrix is written to HBM.  Longer sequences: the fused dequant + tcgen05 GEMM kernel (csrc/prefill_tc.cuh), which
-        # also never materialises the fp16 matrix; shapes it does not take (bits > 4, K % 256 != 0) go dequant -> cuBLAS
-        # like the reference.
+        # also never materialises the fp16 matrix, up to the measured cross-over token count; beyond it, and for shapes
+        # the kernel does not take (bits > 4, K % 256 != 0): dequant -> cuBLAS like the reference.
         T = x.shape[1]
         if T <= 8 and x.dtype == torch.float16 and x.is_cuda:
             out = torch.empty((T, 1, self.out_features), dtype=torch.float16, device=x.device)
             anyprec_gemv(x.reshape(T, 1, self.in_features).contiguous(), self.qweight, self.lut, out, self.bitwidth)
             return out.reshape(1, T, self.out_features)
-        if x.dtype == torch.float16 and x.is_cuda and ap_gemv.prefill_supported(self.qweight, self.bitwidth):
+        if x.dtype == torch.float16 and x.is_cuda and ap_gemv.prefill_prefers_fused(self.qweight, self.bitwidth, T):
             return ap_gemv.anyprec_prefill_gemm(x, self.qweight, self.lut, self.bitwidth)
         weight = anyprec_dequant(self.qweight, self.lut, self.bitwidth)
         return torch.matmul(x, weight.T)

@@ -55,7 +55,7 @@ class AnyPrecisionLinear(nn.Module):
             out = torch.empty((T, 1, self.out_features), dtype=torch.float16, device=x.device)
             anyprec_gemv(x.to(torch.float16).reshape(T, 1, -1).contiguous(), self.qweight, lut, out, w_bits)
             x = out.to(x.dtype).reshape(*x.shape[:-1], self.out_features)
-        elif T > 1 and x.is_cuda and ap_gemv.prefill_supported(self.qweight, w_bits):
+        elif T > 1 and x.is_cuda and ap_gemv.prefill_prefers_fused(self.qweight, w_bits, T):
             # fused dequant + tensor-core GEMM: the fp16 weight matrix is never written to HBM (csrc/prefill_tc.cuh)
             x = ap_gemv.anyprec_prefill_gemm(x.to(torch.float16), self.qweight, lut, w_bits).to(x.dtype)
         elif T > 1:

@@ -18,7 +18,7 @@ import torch
 
 from . import _lib
 
-__all__ = ["anyprec_gemv", "anyprec_dequant", "anyprec_gemv_ex", "anyprec_prefill_gemm", "prefill_supported"]
+__all__ = ["anyprec_gemv", "anyprec_dequant", "anyprec_gemv_ex", "anyprec_prefill_gemm", "prefill_supported", "prefill_prefers_fused"]
 
 
 def _req(cond: bool, msg: str) -> None:
@@ -105,6 +105,20 @@ def anyprec_dequant(qweight: torch.Tensor, lut: torch.Tensor, bitwidth: int) -> 
 def prefill_supported(qweight: torch.Tensor, bitwidth: int) -> bool:
     """shapes the fused tensor-core prefill kernel takes (include/apgemv_b200.h, apg_prefill_gemm)"""
     return 2 <= bitwidth <= 4 and (qweight.size(2) * 32) % 256 == 0
+
+
+# Measured cross-over (B200, profiles/r2_prefill_fused_vs_dequant_matmul.jsonl): the fused kernel dequantises every weight
+# once per 256-token tile, the reference route once per call but pays an fp16 [N, K] write + read.  Fused wins while that
+# HBM round trip dominates, i.e. up to these token counts: (N*K < 40M, N*K >= 40M) per bit-width.
+_FUSED_MAX_TOKENS = {2: (128, 1024), 3: (64, 512), 4: (32, 128)}
+
+
+def prefill_prefers_fused(qweight: torch.Tensor, bitwidth: int, tokens: int) -> bool:
+    """True when `anyprec_prefill_gemm` is the faster route for `tokens` rows of input (else: anyprec_dequant + matmul)"""
+    if not prefill_supported(qweight, bitwidth):
+        return False
+    N, K = qweight.size(1), qweight.size(2) * 32
+    return tokens <= _FUSED_MAX_TOKENS[bitwidth][1 if N * K >= 40_000_000 else 0]
 
 
 _workspaces: dict = {}  # (device index, stream) -> fp32 scratch of the split-K partial sums, grown on demand

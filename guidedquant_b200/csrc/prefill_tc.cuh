@@ -41,7 +41,7 @@ constexpr int MMA_WARP = DQ_WARPS + 1;        // MMA issuer, owns the TMEM alloc
 constexpr int THREADS = (DQ_WARPS + 2) * 32;
 constexpr int MAX_STAGES = 8;
 constexpr uint32_t CTRL_BYTES = 256;          // barriers + TMEM base, at the very start of dynamic shared memory
-constexpr uint32_t TBL_ABS = 2048;            // ABSOLUTE shared address of the lookup tables: an LDS immediate
+constexpr uint32_t TBL_ABS = 2048;            // shared-WINDOW-relative address of the lookup tables: an LDS immediate
 constexpr uint32_t A_COLS = BK / 2;            // TMEM columns of one A stage (two fp16 per 32-bit column)
 constexpr uint32_t SMEM_LIMIT = 227u * 1024u;
 constexpr long long WATCHDOG_CYCLES = 6000000000ll;  // ~3 s: a wait that long is a bug; trap instead of hanging the GPU
@@ -169,7 +169,8 @@ __device__ __forceinline__ uint32_t and_or(uint32_t a, uint32_t m, uint32_t c) {
     asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(d) : "r"(a), "r"(m), "r"(c));
     return d;
 }
-// table word of index byte B of `idx`: address = TBL_ABS + index * 256 + lanebase (lanebase < 256), formed by ONE PRMT
+// table word of index byte B of `idx`: address = lanebase + TBL_ABS + index * 256 (lanebase = window base + a lane offset < 256:
+// its byte 1 is zero), formed by ONE PRMT
 template <int B>
 __device__ __forceinline__ uint32_t lookup(uint32_t idx, uint32_t lanebase) {
     return lds_b32_imm<(int)TBL_ABS>(__byte_perm(idx, lanebase, 0x7604u | (B << 4)));
@@ -297,11 +298,15 @@ __global__ void __launch_bounds__(THREADS, 1) prefill_tc_kernel(const __grid_con
     const uint32_t s0 = smem_u32(ptc_smem);
     // control block: full[MAX_STAGES], empty[MAX_STAGES], accum, tmem base
     const uint32_t bar_full = s0, bar_empty = s0 + 8 * MAX_STAGES, bar_accum = s0 + 16 * MAX_STAGES, tmem_slot = bar_accum + 8;
-    const uint32_t b_base = Lay<BITS>::STAGE_BASE;
+    // base of this CTA's shared window: 0 for a plain launch, rank-dependent (far above 256 KB) inside a cluster (measured:
+    // an absolute layout traps in cluster rank 1).  Tables and token tiles sit at FIXED offsets from it, so that a table
+    // address is window base + LDS immediate + index byte.
+    const uint32_t win = s0 & 0xFFFC0000u;
+    const uint32_t b_base = win + Lay<BITS>::STAGE_BASE;
     const uint32_t b_tile = p.t_tile * (BK * 2);
     uint32_t dyn_size;
     asm("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn_size));
-    if (s0 + CTRL_BYTES > TBL_ABS || b_base + p.stages * b_tile > s0 + dyn_size) {
+    if (s0 - win + CTRL_BYTES > TBL_ABS || b_base + p.stages * b_tile > s0 + dyn_size) {
         if (threadIdx.x == 0) printf("prefill_tc: shared memory layout does not fit (base %u, size %u)\n", s0, dyn_size);
         __trap();
     }
@@ -322,11 +327,16 @@ __global__ void __launch_bounds__(THREADS, 1) prefill_tc_kernel(const __grid_con
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(p.tmem_cols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    uint4 cur[BITS];
     if (warp < DQ_WARPS) {
         // lookup tables of this CTA's 128 rows: warps w and w+4 share rows 32*(w&3)..+31 and build half of the entries each
         const uint32_t row = (warp & 3) * 32 + lane;
         const uint32_t grow = min(row0 + row, p.N - 1);
-        const uint32_t tbl = TBL_ABS + (((warp & 3) >> 1) << Cfg<BITS>::ENTRY_BITS) * 256 + (warp & 1) * 128 + lane * 4;
+        // the first packed words of the row are requested before anything else: their DRAM latency hides the set-up
+        const uint4 *wrow0 = reinterpret_cast<const uint4 *>(p.W) + (size_t)grow * (p.K >> 7) + (warp >> 2);
+#pragma unroll
+        for (int j = 0; j < BITS; j++) cur[j] = ldg_stream_v4(wrow0 + j * ((size_t)p.N * (p.K >> 7)) + 2 * (size_t)sb0);
+        const uint32_t tbl = win + TBL_ABS + (((warp & 3) >> 1) << Cfg<BITS>::ENTRY_BITS) * 256 + (warp & 1) * 128 + lane * 4;
         Net<BITS>::build(p.lut + (size_t)grow * (1u << BITS), tbl, warp >> 2);
     }
     tc_fence_before();
@@ -341,7 +351,7 @@ __global__ void __launch_bounds__(THREADS, 1) prefill_tc_kernel(const __grid_con
         const uint32_t row = (warp & 3) * 32 + lane;
         const uint32_t grow = min(row0 + row, p.N - 1);
         const uint32_t wc = ((warp & 3) >> 1) * (BITS == 3 ? 0x40404040u : 0x10101010u);
-        const uint32_t lb = (warp & 1) * 128 + lane * 4;
+        const uint32_t lb = win + (warp & 1) * 128 + lane * 4;  // bytes 2,3 = window base, byte 1 = 0 (index goes there)
         const uint32_t wpr4 = p.K >> 7;  // uint4 per row and plane
         const uint4 *wrow = reinterpret_cast<const uint4 *>(p.W) + (size_t)grow * wpr4 + h;
         const size_t plane4 = (size_t)p.N * wpr4;
@@ -349,9 +359,7 @@ __global__ void __launch_bounds__(THREADS, 1) prefill_tc_kernel(const __grid_con
         // and, of a stage, the 16 columns of its 4 words
         const uint32_t a_tmem = tmem_base + (((warp & 3) * 32) << 16) + p.t_tile + h * 16;
 
-        uint4 cur[BITS], nxt[BITS];
-#pragma unroll
-        for (int j = 0; j < BITS; j++) cur[j] = ldg_stream_v4(wrow + j * plane4 + 2 * (size_t)sb0);
+        uint4 nxt[BITS];
         uint32_t s = 0, ph = 0;
         for (uint32_t sb = sb0; sb < sb1; sb++) {
             const uint32_t sbn = min(sb + 1, sb1 - 1);

@@ -271,3 +271,31 @@ def test_llama3_rope_table_matches_transformers():
     except Exception as e:  # config spelling differs between transformers versions
         pytest.skip(f"transformers llama3 rope init not callable here: {e}")
     assert scale == 1.0 and torch.allclose(ours, ref.float(), rtol=1e-6, atol=0)
+
+
+def test_prefill_route_selection_follows_the_measured_crossover():
+    """ap_gemv.prefill_prefers_fused: fused tcgen05 kernel for few tokens / large matrices, dequant + matmul beyond the
+    measured cross-over (profiles/r2_prefill_fused_vs_dequant_matmul.jsonl) and for shapes the kernel does not take"""
+    import json
+    import os
+
+    import torch
+
+    from guidedquant_b200 import ap_gemv
+
+    def q(bits, N, K):
+        return torch.empty((bits, N, K // 32), dtype=torch.int32, device="meta")
+
+    assert ap_gemv.prefill_prefers_fused(q(2, 4096, 4096), 2, 64)
+    assert not ap_gemv.prefill_prefers_fused(q(2, 4096, 4096), 2, 2048)
+    assert ap_gemv.prefill_prefers_fused(q(2, 28672, 4096), 2, 1024)
+    assert not ap_gemv.prefill_prefers_fused(q(4, 28672, 4096), 4, 1024)
+    assert not ap_gemv.prefill_prefers_fused(q(5, 4096, 4096), 5, 16)       # bits > 4
+    assert not ap_gemv.prefill_prefers_fused(q(2, 4096, 4096 + 128), 2, 16)  # K % 256 != 0
+    # the table agrees with the committed measurements: wherever it picks the fused kernel, the kernel was not slower
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "r2_prefill_fused_vs_dequant_matmul.jsonl")
+    rows = [json.loads(l) for l in open(path)]
+    assert len(rows) >= 90
+    picked = [r for r in rows if ap_gemv.prefill_prefers_fused(q(r["bits"], r["N"], r["K"]), r["bits"], r["T"])]
+    assert len(picked) >= 40
+    assert all(r["speedup"] >= 0.95 for r in picked), [r for r in picked if r["speedup"] < 0.95]

@@ -115,8 +115,9 @@ def test_aplinear_prefill_uses_the_fused_kernel_and_matches_dequant_matmul():
     from guidedquant_b200 import ap_gemv
     from guidedquant_b200.APLinear import APLinear
 
-    N, K, T, bits = 512, 1024, 40, 4
+    N, K, T, bits = 512, 1024, 24, 4
     q, lut, x = _synth(N, K, bits, T, seed=21)
+    assert ap_gemv.prefill_prefers_fused(q, bits, T)
     lin = APLinear(K, N, bits, device="cuda")
     lin.qweight.copy_(q)
     lin.lut.copy_(lut)
