@@ -28,7 +28,7 @@ EXPORTS = (
     "apg_version", "apg_status_string", "apg_last_cuda_error", "apg_gemv", "apg_gemv_ex", "apg_dequant",
     "apg_round_f32_to_f16", "apg_prefetch_hint", "apg_gemv_fused", "apg_gemv_fused_push", "apg_allreduce_finish",
     "apd_embed", "apd_attn_decode", "apd_lm_head", "apd_argmax_advance", "apd_argmax_advance_tp",
-    "apd_sample_topk_advance", "apg_plan_fast",
+    "apd_sample_topk_advance", "apd_sample_topk_advance_tp", "apg_plan_fast",
     "apg_persist_job_bytes", "apg_persist_smem", "apg_persist_job_gemv", "apg_persist_job_attn", "apg_persist_job_pack",
     "apg_persist_job_reduce", "apg_persist_launch", "apg_prefill_plan", "apg_prefill_gemm",
 )
@@ -142,6 +142,8 @@ def lib() -> ctypes.CDLL:
     L.apg_plan_fast.argtypes = [u32, u32, i32, i32, i32, ctypes.POINTER(u32 * 16)]
     L.apd_sample_topk_advance.restype = i32
     L.apd_sample_topk_advance.argtypes = [vp, u32, f32, u32, vp, vp, vp, vp, u32, u32, vp]
+    L.apd_sample_topk_advance_tp.restype = i32
+    L.apd_sample_topk_advance_tp.argtypes = [vp, u32, f32, u32, vp, u32, u32, ctypes.POINTER(vp), u32, vp, vp, vp, vp, u32, u32, vp]
     L.apg_gemv_fused_push.restype = i32
     L.apg_gemv_fused_push.argtypes = [vp, vp, vp, u32, u32, i32, vp, ctypes.c_float, i32, u32, u32,
                                       ctypes.POINTER(vp), vp, vp, u32, vp]

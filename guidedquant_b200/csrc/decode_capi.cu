@@ -119,4 +119,23 @@ int apd_sample_topk_advance(const void *logits, uint32_t V, float temperature, u
                   static_cast<const __half *>(logits), V, temperature, top_k, seed, token, pos, history, history_len);
 }
 
+int apd_sample_topk_advance_tp(const void *logits, uint32_t V_local, float temperature, uint32_t top_k,
+                               const unsigned long long *seed, uint32_t world, uint32_t rank, void *const *peer_slots,
+                               uint32_t slot_stride, uint32_t *epoch, int *token, int *pos, int *history, uint32_t history_len,
+                               uint32_t flags, void *stream) {
+    if (!logits || !seed || !token || !pos || !peer_slots || !epoch) return APG_ERR_NULL;
+    if (V_local == 0 || !(temperature >= 0.f) || world < 2 || world > 8 || rank >= world) return APG_ERR_SHAPE;
+    if (!al(logits, 16) || !al(seed, 8)) return APG_ERR_ALIGN;
+    if ((uint64_t)top_k >= (uint64_t)V_local * world) top_k = 0;  // no filter, like the single-GPU sampler
+    if (top_k > apd::kSampleTpMaxK || top_k >= V_local || top_k + 2 > slot_stride) return APG_ERR_UNSUPPORTED;
+    uint2 *pp[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    for (uint32_t i = 0; i < world; i++) {
+        if (!peer_slots[i] || !al(peer_slots[i], 8)) return APG_ERR_ALIGN;
+        pp[i] = static_cast<uint2 *>(peer_slots[i]);
+    }
+    return launch(apd::sample_topk_advance_tp_kernel, dim3(1), dim3(apd::kSampleThreads), 0, flags, stream,
+                  static_cast<const __half *>(logits), V_local, temperature, top_k, seed, world, rank, pp[0], pp[1], pp[2], pp[3],
+                  pp[4], pp[5], pp[6], pp[7], slot_stride, epoch, token, pos, history, history_len);
+}
+
 }  // extern "C"

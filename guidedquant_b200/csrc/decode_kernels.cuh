@@ -658,4 +658,199 @@ __global__ void __launch_bounds__(kSampleThreads) sample_topk_advance_kernel(con
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// The same sampler for a VOCAB-SHARDED lm_head (tensor parallel): every rank holds logits[rank*V : (rank+1)*V].  Two
+// packet exchanges over the peers' buffers (data-with-flag stores, like argmax_advance_tp_kernel):
+//   1. top-k pivot: every rank pushes the keys of ITS k largest logits (k packets); the k-th largest of the union of those
+//      world*k keys is the k-th largest of the whole vocabulary, so every rank finds the same global pivot;
+//   2. winner: every rank pushes its best (score, global index) among its logits >= pivot; the global winner is picked
+//      with the same tie rule on every rank.
+// The noise u_i is hashed from the GLOBAL index, so the token equals what sample_topk_advance_kernel draws from the
+// gathered logits (tested in tests/dist_check.py).  Slot layout of a rank's buffer: uint2 [world][slot_stride]; packets
+// 0..k-1 = keys, k and k+1 = (score, index).  Requires top_k <= kSampleTpMaxK, top_k < V, top_k + 2 <= slot_stride.
+// ------------------------------------------------------------------------------------------------------------
+constexpr uint32_t kSampleTpMaxK = 256;
+
+__device__ __forceinline__ void ll_push(uint2 *dst, uint32_t v, uint32_t tag) {
+    asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(dst), "r"(v), "r"(tag) : "memory");
+}
+__device__ __forceinline__ uint32_t ll_poll(const uint2 *src, uint32_t tag) {
+    uint32_t v, t;
+    do {
+        asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(v), "=r"(t) : "l"(src) : "memory");
+    } while (t != tag);
+    return v;
+}
+
+__global__ void __launch_bounds__(kSampleThreads) sample_topk_advance_tp_kernel(
+    const __half *__restrict__ logits, uint32_t V, float temperature, uint32_t top_k, const unsigned long long *__restrict__ seed,
+    uint32_t world, uint32_t rank, uint2 *p0, uint2 *p1, uint2 *p2, uint2 *p3, uint2 *p4, uint2 *p5, uint2 *p6, uint2 *p7,
+    uint32_t slot_stride, uint32_t *epoch, int *token, int *pos, int *history, uint32_t history_len) {
+    apg::pdl_wait_prior_grid();
+    apg::pdl_launch_dependents();
+    uint2 *peers[8] = {p0, p1, p2, p3, p4, p5, p6, p7};
+    __shared__ uint32_t red[32];
+    __shared__ float bv[32];
+    __shared__ int bi[32];
+    __shared__ uint32_t cand_idx[kSampleCap];
+    __shared__ unsigned short cand_key[kSampleCap];
+    __shared__ unsigned short top_keys[kSampleTpMaxK];
+    __shared__ unsigned short all_keys[8 * kSampleTpMaxK];
+    __shared__ uint32_t n_cand, n_top;
+    const uint32_t lane = threadIdx.x & 31u;
+    const int p = *pos;
+    const unsigned long long sd = *seed;
+    const float t = fmaxf(temperature, 1e-5f);
+    const uint32_t ep = *epoch + 1u;
+    const uint32_t goff = rank * V;  // global index of local logit 0
+
+    uint32_t pivot = 1u, ncand = 0u;
+    bool use_list = false;
+    if (top_k > 0) {
+        // ---- local k-th largest key (as on one GPU) ----
+        uint32_t mk = 0;
+        for_each_logit(logits, V, [&](uint32_t, uint32_t h, bool ok) {
+            if (ok) mk = max(mk, f16_order_key(h));
+        });
+        mk = block_max_u32(mk, red);
+        const uint32_t wlo = mk > kSampleWindow ? mk - kSampleWindow : 1u;
+        if (threadIdx.x == 0) n_cand = 0, n_top = 0;
+        __syncthreads();
+        for_each_logit(logits, V, [&](uint32_t i, uint32_t h, bool ok) {
+            const uint32_t key = f16_order_key(h);
+            const bool in = ok && key >= wlo;
+            const uint32_t m = __ballot_sync(0xffffffffu, in);
+            if (m) {
+                const int leader = __ffs(m) - 1;
+                uint32_t base = 0;
+                if ((int)lane == leader) base = atomicAdd(&n_cand, (uint32_t)__popc(m));
+                base = __shfl_sync(0xffffffffu, base, leader);
+                const uint32_t slot = base + __popc(m & ((1u << lane) - 1u));
+                if (in && slot < kSampleCap) cand_idx[slot] = i, cand_key[slot] = (unsigned short)key;
+            }
+        });
+        __syncthreads();
+        ncand = n_cand;
+        use_list = ncand >= top_k && ncand <= kSampleCap;
+        uint32_t lo = use_list ? wlo : 0u, hi = mk;
+        while (lo < hi) {
+            const uint32_t mid = (lo + hi + 1u) >> 1;
+            uint32_t c = 0;
+            if (use_list) {
+                for (uint32_t j = threadIdx.x; j < ncand; j += blockDim.x) c += (uint32_t)cand_key[j] >= mid;
+            } else {
+                for_each_logit(logits, V, [&](uint32_t, uint32_t h, bool ok) { c += (ok && f16_order_key(h) >= mid) ? 1u : 0u; });
+            }
+            c = block_sum_u32(c, red);
+            if (c >= top_k) lo = mid;
+            else hi = mid - 1u;
+        }
+        // ---- the k largest local keys: every key above the local pivot, the rest of the k slots = the pivot itself ----
+        auto keep = [&](uint32_t key, bool ok) {
+            const bool in = ok && key > lo;
+            const uint32_t m = __ballot_sync(0xffffffffu, in);
+            if (m) {
+                const int leader = __ffs(m) - 1;
+                uint32_t base = 0;
+                if ((int)lane == leader) base = atomicAdd(&n_top, (uint32_t)__popc(m));
+                base = __shfl_sync(0xffffffffu, base, leader);
+                const uint32_t slot = base + __popc(m & ((1u << lane) - 1u));
+                if (in && slot < top_k) top_keys[slot] = (unsigned short)key;
+            }
+        };
+        if (use_list) {
+            for (uint32_t j0 = threadIdx.x & ~31u; j0 < ncand; j0 += blockDim.x) {
+                const uint32_t j = j0 + lane;
+                keep(j < ncand ? (uint32_t)cand_key[j] : 0u, j < ncand);
+            }
+        } else {
+            for_each_logit(logits, V, [&](uint32_t, uint32_t h, bool ok) { keep(f16_order_key(h), ok); });
+        }
+        __syncthreads();
+        const uint32_t above = min(n_top, top_k);  // < top_k by the definition of the pivot
+        for (uint32_t j = above + threadIdx.x; j < top_k; j += blockDim.x) top_keys[j] = (unsigned short)lo;
+        __syncthreads();
+        // ---- exchange 1: keys ----
+        for (uint32_t e = threadIdx.x; e < world * top_k; e += blockDim.x) {
+            const uint32_t pr = e / top_k, j = e % top_k;
+            ll_push(peers[pr] + (size_t)rank * slot_stride + j, top_keys[j], ep);
+        }
+        for (uint32_t e = threadIdx.x; e < world * top_k; e += blockDim.x) {
+            const uint32_t r = e / top_k, j = e % top_k;
+            all_keys[e] = (unsigned short)ll_poll(peers[rank] + (size_t)r * slot_stride + j, ep);
+        }
+        __syncthreads();
+        uint32_t glo = 0u, ghi = 0xffffu;
+        while (glo < ghi) {  // largest g with count(all_keys >= g) >= top_k
+            const uint32_t mid = (glo + ghi + 1u) >> 1;
+            uint32_t c = 0;
+            for (uint32_t j = threadIdx.x; j < world * top_k; j += blockDim.x) c += (uint32_t)all_keys[j] >= mid;
+            c = block_sum_u32(c, red);
+            if (c >= top_k) glo = mid;
+            else ghi = mid - 1u;
+        }
+        pivot = max(glo, 1u);  // >= the local pivot, so the candidate list (keys >= wlo) still covers everything kept
+    }
+
+    float best = -CUDART_INF_F;
+    int idx = 0x7fffffff;
+    auto consider = [&](uint32_t i, uint32_t key) {
+        const float u = sample_uniform(sd, (uint32_t)p, goff + i);
+        const float s = f16_key_value(key) / t - logf(-logf(u));
+        if (better(s, (int)(goff + i), best, idx)) best = s, idx = (int)(goff + i);
+    };
+    if (use_list) {
+        for (uint32_t j = threadIdx.x; j < ncand; j += blockDim.x)
+            if ((uint32_t)cand_key[j] >= pivot) consider(cand_idx[j], cand_key[j]);
+    } else {
+        for_each_logit(logits, V, [&](uint32_t i, uint32_t h, bool ok) {
+            const uint32_t key = f16_order_key(h);
+            if (ok && key >= pivot) consider(i, key);
+        });
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+        if (better(ob, oi, best, idx)) best = ob, idx = oi;
+    }
+    const uint32_t w = threadIdx.x >> 5;
+    if (lane == 0) bv[w] = best, bi[w] = idx;
+    __syncthreads();
+    if (w != 0) return;
+    best = lane < (blockDim.x >> 5) ? bv[lane] : -CUDART_INF_F;
+    idx = lane < (blockDim.x >> 5) ? bi[lane] : 0x7fffffff;
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+        if (better(ob, oi, best, idx)) best = ob, idx = oi;
+    }
+    // ---- exchange 2: (score, global index) of this rank's winner ----
+    if (lane < world) {
+        uint2 *dst = peers[lane] + (size_t)rank * slot_stride + top_k;
+        ll_push(dst, __float_as_uint(best), ep);
+        ll_push(dst + 1, (uint32_t)idx, ep);
+    }
+    float gv = -CUDART_INF_F;
+    int gi = 0x7fffffff;
+    if (lane < world) {
+        const uint2 *src = peers[rank] + (size_t)lane * slot_stride + top_k;
+        gv = __uint_as_float(ll_poll(src, ep));
+        gi = (int)ll_poll(src + 1, ep);
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, gv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, gi, o);
+        if (better(ob, oi, gv, gi)) gv = ob, gi = oi;
+    }
+    if (lane == 0) {
+        *token = gi;
+        if (history && (uint32_t)(p + 1) < history_len) history[p + 1] = gi;
+        *pos = p + 1;
+        *epoch = ep;
+    }
+}
+
 }  // namespace apd

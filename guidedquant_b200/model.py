@@ -371,7 +371,14 @@ class APTransformer:
                                  self.best_idx.data_ptr(), ctypes.byref(npart), self.rank * self.V_l,
                                  fl & ~self.lm_head_no_pdl, st), "apd_lm_head")
           self._npart = npart.value
-        if "sample" not in self.debug_skip and self.push is not None:
+        if "sample" not in self.debug_skip and self.push is not None and self.temperature > 0.0:
+          site = 2 * c["n_layer"]   # vocab-sharded sampling: top-k pivot + winner exchanged through the peers' buffers
+          _lib.check(L.apd_sample_topk_advance_tp(self.logits.data_ptr(), self.V_l, float(self.temperature), int(self.top_k or 0),
+                                                self.seed.data_ptr(), self.world, self.rank, self.push.site_ptrs(site),
+                                                self.push.n_max, self.push.epoch_ptr(site), self.token.data_ptr(),
+                                                self.pos.data_ptr(), self.history.data_ptr(), self.history.numel(), fl, st),
+                     "apd_sample_topk_advance_tp")
+        elif "sample" not in self.debug_skip and self.push is not None:
           site = 2 * c["n_layer"]
           _lib.check(L.apd_argmax_advance_tp(self.best_val.data_ptr(), self.best_idx.data_ptr(), self._npart, self.world,
                                            self.rank, self.push.site_ptrs(site), self.push.epoch_ptr(site),
@@ -391,8 +398,10 @@ class APTransformer:
     def set_sampling(self, temperature: float = 0.0, top_k: int | None = None, seed: int | None = None):
         """temperature / top_k of the reference's sample() (generate.py:55-73).  temperature 0 (the reference CLI default,
         generate.py:400) keeps the greedy kernel.  Changing temperature / top_k drops the captured graph; a new seed does not."""
-        if temperature > 0.0 and self.world > 1:
-            raise NotImplementedError("temperature sampling needs the full logits; lm_head is vocab-sharded under tensor parallelism")
+        if temperature > 0.0 and self.world > 1 and top_k is not None and top_k < self.cfg["vocab"]:
+            # vocab-sharded sampler (apd_sample_topk_advance_tp): every rank contributes its k largest logits to the pivot
+            if not (0 < top_k <= 256 and top_k < self.V_l and top_k + 2 <= self.cfg["dim"]):
+                raise ValueError(f"tensor-parallel top-k sampling needs top_k <= min(256, vocab/world - 1, dim - 2), got {top_k}")
         if (float(temperature), top_k) != (self.temperature, self.top_k):
             self.temperature, self.top_k, self.graph = float(temperature), top_k, None
         if seed is not None:

@@ -48,10 +48,21 @@ int apd_argmax_advance_tp(const float *best_val, const int *best_idx, uint32_t n
  * kept, like the reference's `logits < pivot` mask; top_k == 0 or >= V: no filter), q_i = -log(u_i), u_i a counter hash
  * of (*seed, *pos, i) - a fixed documented stream, not torch's Philox (restated in oracle/decode_oracle.py).  Then
  * history[*pos + 1] = *token and *pos += 1 like apd_argmax_advance.  seed: device uint64; logits 16-byte aligned.
- * Single GPU (a vocab-sharded lm_head has no global top-k). */
+ * Single GPU; apd_sample_topk_advance_tp is the vocab-sharded form. */
 int apd_sample_topk_advance(const void *logits, uint32_t V, float temperature, uint32_t top_k,
                             const unsigned long long *seed, int *token, int *pos, int *history, uint32_t history_len,
                             uint32_t flags, void *stream);
+
+/* The same sampler for a vocab-sharded lm_head (tensor parallel, `logits` = this rank's V_local logits of global indices
+ * rank*V_local ..): two data-with-flag packet exchanges through the peers' buffers (peer_slots[r] = rank r's uint2
+ * [world][slot_stride] exchange buffer, zero-initialised; *epoch advanced by the call) — the k largest keys of every rank
+ * give the global top-k pivot, then every rank's best (score, global index) gives the winner.  The noise is hashed from the
+ * GLOBAL index, so the token is the one apd_sample_topk_advance draws from the gathered logits.  top_k <= 256,
+ * top_k < V_local (or >= the whole vocabulary = no filter), top_k + 2 <= slot_stride; else APG_ERR_UNSUPPORTED. */
+int apd_sample_topk_advance_tp(const void *logits, uint32_t V_local, float temperature, uint32_t top_k,
+                               const unsigned long long *seed, uint32_t world, uint32_t rank, void *const *peer_slots,
+                               uint32_t slot_stride, uint32_t *epoch, int *token, int *pos, int *history, uint32_t history_len,
+                               uint32_t flags, void *stream);
 
 #ifdef __cplusplus
 }

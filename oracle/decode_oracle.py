@@ -127,3 +127,31 @@ def sample_topk_scores(logits_f16, temperature: float, top_k, seed: int, pos: in
     s = np.where(np.isnan(l), -np.inf, s)
     q = -np.log(sample_uniform(seed, pos, n))
     return s - np.log(q), q
+
+
+def sample_topk_sharded(logits_f16, temperature: float, top_k, seed: int, pos: int, world: int):
+    """The vocab-sharded sampler's algorithm (apd_sample_topk_advance_tp, csrc/decode_kernels.cuh) restated on the CPU:
+    every rank contributes its k largest logits, the k-th largest of that union is the global pivot, every rank then
+    proposes its best score among its logits >= pivot, and the best proposal (ties: smaller global index) wins.
+    Must equal argmax(sample_topk_scores(...)) on the unsharded logits — checked in tests/test_decode_oracle_cpu.py."""
+    import numpy as np
+
+    l = np.asarray(logits_f16, dtype=np.float16).astype(np.float64)
+    n = l.shape[0]
+    assert n % world == 0
+    vl = n // world
+    t = max(temperature, 1e-5)
+    pivot = -np.inf
+    if top_k is not None and 0 < top_k < n:
+        assert top_k < vl
+        union = np.concatenate([np.sort(l[r * vl:(r + 1) * vl])[::-1][:top_k] for r in range(world)])
+        pivot = np.sort(union)[::-1][top_k - 1]
+    q = -np.log(sample_uniform(seed, pos, n))  # hashed from the GLOBAL index
+    best = (-np.inf, n)
+    for r in range(world):
+        sl = l[r * vl:(r + 1) * vl]
+        s = np.where(sl < pivot, -np.inf, sl / t) - np.log(q[r * vl:(r + 1) * vl])
+        i = int(np.argmax(s))  # first maximum = smallest index
+        if s[i] > best[0] or (s[i] == best[0] and r * vl + i < best[1]):
+            best = (s[i], r * vl + i)
+    return best[1]

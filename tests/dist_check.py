@@ -136,6 +136,31 @@ def main():
             dist.all_gather_object(toks_all, toks_tp)
             assert all(t == toks_all[0] for t in toks_all), "ranks generated different tokens"
             log(f"TP decode ({engine} engine) vs single GPU: worst logit err", worst, "tokens", toks_tp[:8])
+            # ---- vocab-sharded temperature / top-k sampling == the single-GPU sampler on the gathered logits, every token
+            L = _lib.lib()
+            for (temp, k) in ((0.8, 8), (1.3, None), (0.7, 1)):
+                tp.set_sampling(temp, k, seed=77 + (k or 0))
+                tp.reset(1)
+                for it in range(5):
+                    pos_before = tp.pos_host()
+                    tp.step()
+                    tp.stream.synchronize()
+                    tok = int(tp.token.cpu()[0])
+                    parts = [torch.zeros_like(tp.logits) for _ in range(world)]
+                    dist.all_gather(parts, tp.logits)
+                    torch.cuda.synchronize()
+                    full_logits = torch.cat(parts).contiguous()
+                    t1 = torch.zeros(1, dtype=torch.int32, device=dev)
+                    p1 = torch.full((1,), pos_before, dtype=torch.int32, device=dev)
+                    _lib.check(L.apd_sample_topk_advance(full_logits.data_ptr(), full_logits.numel(), temp, k or 0, tp.seed.data_ptr(),
+                                                         t1.data_ptr(), p1.data_ptr(), None, 0, 0,
+                                                         torch.cuda.current_stream().cuda_stream), "sample")
+                    torch.cuda.synchronize()
+                    assert int(t1.cpu()[0]) == tok, (engine, temp, k, it, int(t1.cpu()[0]), tok)
+                    if k == 1:  # top-1 sampling is greedy
+                        assert tok == int(torch.argmax(full_logits.float())) or err_margin(full_logits.float())
+            tp.set_sampling(0.0, None)
+            log(f"TP sampling ({engine} engine): every token equals the single-GPU sampler on the gathered logits")
             tp.graph = None
             full.graph = None
             del tp, full

@@ -59,3 +59,20 @@ def test_sampling_oracle_equals_reference_formulation():
             assert np.array_equal(np.isfinite(s), (probs > 0).numpy() | np.isfinite(s))  # kept set ⊇ non-zero probs
             if top_k is not None and top_k < V:
                 assert np.isfinite(s).sum() >= top_k
+
+
+def test_sharded_sampler_algorithm_equals_the_unsharded_one():
+    """the two-exchange scheme of the tensor-parallel sampler (k largest keys per rank -> global pivot; per-rank best ->
+    winner) picks the token the single-GPU sampler picks, for every world size, with ties at the pivot"""
+    import numpy as np
+
+    from oracle import decode_oracle as D
+
+    rng = np.random.default_rng(3)
+    for V, k, temp in ((1024, 8, 0.8), (4096, 32, 1.0), (2048, 1, 0.5), (1024, None, 1.3), (512, 5, 0.9)):
+        logits = rng.standard_normal(V).astype(np.float16)
+        logits[rng.integers(0, V, 40)] = np.float16(1.5)  # many ties, some of them at the pivot for small k
+        for world in (2, 4, 8):
+            for pos in range(4):
+                s, _ = D.sample_topk_scores(logits, temp, k, 1234, pos)
+                assert D.sample_topk_sharded(logits, temp, k, 1234, pos, world) == int(np.argmax(s)), (V, k, world, pos)
