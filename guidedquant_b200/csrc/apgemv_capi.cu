@@ -73,20 +73,14 @@ template <int BITS>
 bool plan_fast(uint32_t N, uint32_t K, int ctas_per_sm, int sms, FastPlan *pl) {
     const uint32_t nchunk = (K + 1023u) / 1024u;
     if (nchunk > 32) return false;
-    static const uint32_t cpw_thresh = getenv("APG_CPW_THRESH") ? (uint32_t)atoi(getenv("APG_CPW_THRESH")) : 8u;
-    pl->cpw = nchunk > cpw_thresh ? 2u : 1u;
+    pl->cpw = nchunk > 8u ? 2u : 1u;                             // more than 8 chunks: two chunks per consumer warp
     pl->nwk = (nchunk + pl->cpw - 1) / pl->cpw;                  // <= 16
-    static const uint32_t g_mode = getenv("APG_GROUP_MODE") ? (uint32_t)atoi(getenv("APG_GROUP_MODE")) : 0u;
-    if (g_mode == 0) pl->groups = pl->nwk >= 8 ? 1u : (8u / pl->nwk);   // ~8 consumer warps per CTA
-    else pl->groups = pl->nwk <= 4 ? (8u / pl->nwk) : (pl->nwk <= 8 ? 2u : 1u);  // 5..8 chunk warps: two groups, one CTA/SM
-    static const uint32_t g_force = getenv("APG_GROUPS") ? (uint32_t)atoi(getenv("APG_GROUPS")) : 0u;
-    if (g_force && pl->nwk * g_force <= 16) pl->groups = g_force;
+    pl->groups = pl->nwk >= 8 ? 1u : (8u / pl->nwk);             // ~8 consumer warps per CTA
     const uint32_t ncons = pl->groups * pl->nwk;
     pl->threads = (ncons + 1) * 32u;
     const uint32_t row_bytes = K / 8u * BITS;                     // all planes of one row
     uint32_t rs = 8;
-    static const uint32_t stage_kb = getenv("APG_STAGE_KB") ? (uint32_t)atoi(getenv("APG_STAGE_KB")) : 32u;
-    while (rs > 2 && rs * row_bytes > stage_kb * 1024u) rs >>= 1;  // stage <= APG_STAGE_KB (32 KB measured best; RS = 4 stages are 5-12 % slower)
+    while (rs > 2 && rs * row_bytes > 32u * 1024u) rs >>= 1;      // stage <= 32 KB (measured best; 16 KB stages are 5-12 % slower)
     pl->rs = rs;
     pl->stage_bytes = rs * row_bytes;
     int c = ctas_per_sm > 0 ? ctas_per_sm : (ncons <= 8 ? 2 : 1);
@@ -97,8 +91,7 @@ bool plan_fast(uint32_t N, uint32_t K, int ctas_per_sm, int sms, FastPlan *pl) {
     pl->grid = grid;
     // rows are dealt in half stages: with whole stages an SM ends up with e.g. 4 stages against an average of 3.46
     // (N = 4096, RS = 8, 296 CTAs); a trailing half stage runs the half-length row loop
-    static const uint32_t half_stage = getenv("APG_HALF_STAGE") ? (uint32_t)atoi(getenv("APG_HALF_STAGE")) : 1u;
-    pl->unit_rows = half_stage ? rs / 2u : rs;
+    pl->unit_rows = rs / 2u;
     pl->tot_units = (N + pl->unit_rows - 1) / pl->unit_rows;
     const uint32_t units_per_cta = (pl->tot_units + grid - 1) / grid;
     const uint32_t stages_per_cta = (units_per_cta * pl->unit_rows + rs - 1) / rs;
@@ -215,8 +208,7 @@ int launch_wide_bits(const void *x, void *out, float *partial, const void *qweig
     // except where the activation traffic dominates anyway (cheap pair-table dequant against 5..8 batch rows).
     // Measured on B200, N = 4096, K = 4096 (us, R=1 / R=2): 2-bit M=2 5.3 / 6.9, 4-bit M=8 14.5 / 18.2, 8-bit M=1 9.6 / 11.5,
     // 2-bit M=8 16.5 / 13.1.
-    static const uint32_t r1_max = getenv("APG_WIDE_R1_MAXN") ? (uint32_t)atoi(getenv("APG_WIDE_R1_MAXN")) : 8192u;
-    if (N <= r1_max && !(BITS <= 3 && M > 4))
+    if (N <= 8192u && !(BITS <= 3 && M > 4))
         return launch_wide_rows<BITS, 1>(x, out, partial, qweight, lut, M, N, K, stream);
     return launch_wide_rows<BITS, 2>(x, out, partial, qweight, lut, M, N, K, stream);
 }

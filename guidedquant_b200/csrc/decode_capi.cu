@@ -65,7 +65,7 @@ int apd_lm_head(const void *x, const void *norm_w, float eps, const void *W, voi
     if (ce == cudaSuccess) ce = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (ce != cudaSuccess) return apg_internal_cuda_fail((int)ce);
     const uint32_t nv = D / 256;
-    static const uint32_t per_sm = getenv("APD_LMHEAD_CTAS") ? (uint32_t)atoi(getenv("APD_LMHEAD_CTAS")) : 6u;  // measured on B200: 2 -> 5.1 TB/s, 4 -> 6.5, 6 -> 6.6
+    const uint32_t per_sm = 6u;  // CTAs per SM, measured on B200: 2 -> 5.1 TB/s, 4 -> 6.5, 6 -> 6.6
     uint32_t grid = (uint32_t)sms * per_sm;
     if (grid * 8u > V) grid = (V + 7) / 8;
     if (n_partials) *n_partials = grid;
