@@ -66,6 +66,9 @@ int make_plan(uint32_t T, uint32_t N, uint32_t K, int bits, int sms, int allow_s
     uint32_t stages = (SMEM_LIMIT - 1024u - base) / per_stage;
     if (stages > MAX_STAGES) stages = MAX_STAGES;
     if (stages > (512u - t_tile) / A_COLS) stages = (512u - t_tile) / A_COLS;
+    // up to 128 tokens per tile: keep accumulator + A ring within 256 TMEM columns, so that TWO CTAs run on an SM at once
+    // (a second CTA would otherwise sit in tcgen05.alloc until the first one exits) and overlap their set-up / epilogue
+    if (t_tile <= 128u && stages > (256u - t_tile) / A_COLS) stages = (256u - t_tile) / A_COLS;
     if (stages < 2) return APG_ERR_UNSUPPORTED;
     pl->stages = stages;
     pl->smem_bytes = base + stages * per_stage;  // dynamic shared memory starts at (or near) shared address 0
