@@ -299,3 +299,35 @@ def test_prefill_route_selection_follows_the_measured_crossover():
     picked = [r for r in rows if ap_gemv.prefill_prefers_fused(q(r["bits"], r["N"], r["K"]), r["bits"], r["T"])]
     assert len(picked) >= 40
     assert all(r["speedup"] >= 0.95 for r in picked), [r for r in picked if r["speedup"] < 0.95]
+
+
+def test_prefill_plan_budgets_hold_for_every_shape():
+    """apg_prefill_plan (host-side planner of the tcgen05 prefill kernel): token tile, ring depth, shared memory, TMEM columns
+    and split-K scratch stay within the hardware budgets for every (T, N, K, bits); unsupported shapes are refused"""
+    import ctypes
+
+    from guidedquant_b200 import _lib
+
+    L = _lib.lib()
+    plan = (ctypes.c_uint32 * 8)()
+    need = ctypes.c_uint64(0)
+    n_ok = 0
+    for bits in (2, 3, 4):
+        tbl = {2: 8192, 3: 32768, 4: 8192}[bits]
+        for K in (256, 1024, 4096, 11008, 14336, 28672):
+            for N in (2, 128, 200, 4096, 6144, 28672):
+                for T in (1, 9, 16, 33, 64, 128, 129, 256, 257, 300, 1000, 2048, 5000):
+                    assert L.apg_prefill_plan(T, N, K, bits, 148, plan, ctypes.byref(need)) == 0, (T, N, K, bits)
+                    t_tile, tok_tiles, row_tiles, splits, stages, smem, tmem, sb = list(plan)
+                    assert t_tile % 32 == 0 and 32 <= t_tile <= 256 and tok_tiles * t_tile >= T > (tok_tiles - 1) * t_tile
+                    assert row_tiles * 128 >= N > (row_tiles - 1) * 128 and sb == K // 256
+                    assert 2 <= stages <= 8 and t_tile + stages * 32 <= tmem <= 512 and tmem & (tmem - 1) == 0
+                    assert 2048 + tbl + stages * t_tile * 128 <= smem <= 227 * 1024 - 1024
+                    assert 1 <= splits <= max(1, sb // 2) and (splits == 1 or row_tiles * tok_tiles * splits <= 148)
+                    assert need.value == (splits * T * N * 4 if splits > 1 else 0)
+                    if t_tile <= 128:
+                        assert tmem <= 256  # two CTAs per SM
+                    n_ok += 1
+    assert n_ok == 3 * 6 * 6 * 13
+    for (T, N, K, bits) in ((16, 128, 128, 2), (16, 128, 4096 + 32, 3), (16, 128, 4096, 5), (0, 128, 4096, 2)):
+        assert L.apg_prefill_plan(T, N, K, bits, 148, plan, ctypes.byref(need)) != 0
