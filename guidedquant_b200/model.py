@@ -351,18 +351,10 @@ class APTransformer:
                 self.push.finish(2 * i + 1, self.x, n2, residual=self.h, flags=fl)
                 self.launches_per_token += 4
 
-    def decode_step(self):
-        """embedding -> L blocks -> lm_head -> greedy sample; reads self.token / self.pos on the device and advances them."""
+    def _head_and_sample(self):
+        """final RMSNorm + lm_head on self.x, then the sampler: writes self.token, history[pos + 1], pos += 1 on the device"""
         L, c, sd, fl = _lib.lib(), self.cfg, self.sd, self.flags
         st = torch.cuda.current_stream().cuda_stream
-        self.launches_per_token = 0
-        if self.engine == "persistent":
-            if self.prog is None:
-                self._build_program()
-            self.prog.launch(self.pos)
-            self.launches_per_token = 1
-        else:
-            self._blocks_launches()
         if "lm_head" not in self.debug_skip:
           import ctypes
           npart = ctypes.c_uint32(0)
@@ -392,7 +384,104 @@ class APTransformer:
           _lib.check(L.apd_argmax_advance(self.best_val.data_ptr(), self.best_idx.data_ptr(), self._npart,
                                         self.token.data_ptr(), self.pos.data_ptr(),
                                         self.history.data_ptr(), self.history.numel(), fl, st), "apd_argmax_advance")
+
+    def decode_step(self):
+        """embedding -> L blocks -> lm_head -> greedy sample; reads self.token / self.pos on the device and advances them."""
+        L, c, sd, fl = _lib.lib(), self.cfg, self.sd, self.flags
+        st = torch.cuda.current_stream().cuda_stream
+        self.launches_per_token = 0
+        if self.engine == "persistent":
+            if self.prog is None:
+                self._build_program()
+            self.prog.launch(self.pos)
+            self.launches_per_token = 1
+        else:
+            self._blocks_launches()
+        self._head_and_sample()
         self.launches_per_token += 2
+
+    # ------------------------------------------------------------------ prompt prefill
+    def _prefill_linear(self, x: torch.Tensor, name: str) -> torch.Tensor:
+        """[T, K] -> [T, N] through the same routes as APLinear.gemm: batched LUT GEMV up to 8 rows, the fused dequant + tcgen05
+        GEMM kernel up to the measured cross-over, dequant -> library matmul beyond"""
+        from . import ap_gemv
+
+        q, lut = self.sd[name + ".qweight"], self.sd[name + ".lut"]
+        T = x.shape[0]
+        if T <= 8:
+            out = torch.empty((T, 1, q.shape[1]), dtype=torch.float16, device=x.device)
+            ap_gemv.anyprec_gemv(x.reshape(T, 1, -1).contiguous(), out, q, lut, self.bits)
+            return out.reshape(T, -1)
+        if ap_gemv.prefill_prefers_fused(q, self.bits, T):
+            return ap_gemv.anyprec_prefill_gemm(x.contiguous(), q, lut, self.bits)
+        return torch.matmul(x, ap_gemv.anyprec_dequant(q, lut, self.bits).T)
+
+    def _rmsnorm(self, x: torch.Tensor, w: torch.Tensor) -> torch.Tensor:  # model.py:280-285: fp32 normalise, cast, * weight
+        xf = x.float()
+        return (xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + self.eps)).to(x.dtype) * w
+
+    @torch.no_grad()
+    def prefill(self, tokens: list[int]) -> int:
+        """Process a whole prompt at once — the reference's prefill (generate.py:146-166: one model forward over the prompt, SDPA
+        with a causal mask, APLinear.gemm for every Linear) — instead of one decode step per prompt token.  The Linears run on
+        the fused tensor-core kernel; the glue (RMSNorm, RoPE, attention, SwiGLU, residuals) is torch with the reference's fp16
+        roundings.  Fills the KV caches, samples the first new token with the decode sampler and leaves the model at position
+        len(tokens); returns that token.  Tensor parallel: K-sharded Linears are summed with one NCCL all-reduce each."""
+        T, c, sd = len(tokens), self.cfg, self.sd
+        assert 1 <= T < self.S, (T, self.S)
+        if self.graph is None:
+            self.capture()   # also lines the ranks up and builds the persistent program
+        import torch.nn.functional as F
+
+        H, Hkv, hd = self.H_l, self.Hkv_l, 128
+
+        def allreduce(y):
+            if self.world == 1:
+                return y
+            yf = y.float()
+            torch.distributed.all_reduce(yf, group=self.pg)
+            return yf.half()
+
+        with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
+            if self.world > 1:
+                self.stream.synchronize()  # no NCCL collective while launches of the persistent engine are in flight
+            tok = torch.tensor(tokens, dtype=torch.long, device=self.device)
+            x = sd["tok_embeddings.weight"][tok]                                   # [T, dim] fp16
+            ang = torch.arange(T, dtype=torch.float32, device=self.device)[:, None] * self.inv_freq[None, :].float()
+            emb = torch.cat((ang, ang), dim=-1)
+            cos, sin = emb.cos().half()[:, None, :], emb.sin().half()[:, None, :]  # fp32 -> fp16 (model.py:396-405)
+
+            def rope(t):  # HF rotate-half in fp16 (model.py:268-272, 309-314)
+                rot = torch.cat((-t[..., hd // 2:], t[..., :hd // 2]), dim=-1)
+                return t * cos + rot * sin
+
+            for i in range(c["n_layer"]):
+                p = f"layers.{i}."
+                qkv = self._prefill_linear(self._rmsnorm(x, sd[p + "input_layernorm.weight"]), p + "attention.wqkv")
+                q = rope(qkv[:, : H * hd].reshape(T, H, hd))
+                k = rope(qkv[:, H * hd: (H + Hkv) * hd].reshape(T, Hkv, hd))
+                v = qkv[:, (H + Hkv) * hd:].reshape(T, Hkv, hd)
+                self.k_cache[i][:, :T] = k.transpose(0, 1)
+                self.v_cache[i][:, :T] = v.transpose(0, 1)
+                kk = k.transpose(0, 1).repeat_interleave(H // Hkv, dim=0)          # GQA (model.py:229-230)
+                vv = v.transpose(0, 1).repeat_interleave(H // Hkv, dim=0)
+                y = F.scaled_dot_product_attention(q.transpose(0, 1)[None], kk[None], vv[None], is_causal=True)[0]
+                y = y.transpose(0, 1).reshape(T, H * hd)
+                h = x + allreduce(self._prefill_linear(y, p + "attention.wo"))
+                gu = self._prefill_linear(self._rmsnorm(h, sd[p + "post_attention_layernorm.weight"]), p + "feed_forward.w1w3")
+                if self.glu_epilogue:   # rows interleaved (gate_i, up_i)
+                    gate, up = gu[:, 0::2], gu[:, 1::2]
+                else:
+                    gate, up = gu[:, : self.inter_l], gu[:, self.inter_l:]
+                x = h + allreduce(self._prefill_linear(F.silu(gate) * up, p + "feed_forward.w2"))
+            # hand over to the decode kernels: last token's hidden state -> lm_head -> sampler (advances pos to T)
+            self.x.copy_(x[T - 1])
+            self.history[:T] = tok.to(torch.int32)
+            self.pos.fill_(T - 1)
+            self._head_and_sample()
+            self._pos_host = T
+        self.stream.synchronize()
+        return int(self.token.cpu()[0])
 
     # ------------------------------------------------------------------ graph + generation
     def set_sampling(self, temperature: float = 0.0, top_k: int | None = None, seed: int | None = None):
@@ -478,16 +567,23 @@ class APTransformer:
 
     @torch.no_grad()
     def generate(self, prompt: list[int], max_new_tokens: int, temperature: float | None = None, top_k: int | None = None,
-                 seed: int | None = None) -> list[int]:
-        """the reference's generate() (generate.py:146-186) with a sequential prefill (prompts are BOS-only in the
-        reference's benchmark protocol, generate.py:310-313).  Greedy unless a temperature > 0 is given / was set."""
+                 seed: int | None = None, prefill: bool = True) -> list[int]:
+        """the reference's generate() (generate.py:146-186): prompts longer than one token go through prefill() (one batched pass,
+        Linears on the fused tensor-core kernel) unless prefill=False (one decode step per prompt token); a BOS-only prompt — the
+        reference's benchmark protocol, generate.py:310-313 — is pure decode.  Greedy unless a temperature > 0 is given / set."""
         assert len(prompt) >= 1 and len(prompt) + max_new_tokens <= self.S
         if temperature is not None:
             self.set_sampling(temperature, top_k, seed)
         elif seed is not None:
             self.set_sampling(self.temperature, self.top_k, seed)
         self.reset(prompt[0])
-        for t in prompt[1:]:  # teacher-forced prefill, one token at a time
+        if prefill and len(prompt) > 1 and max_new_tokens >= 1:
+            self.prefill(prompt)
+            for _ in range(max_new_tokens - 1):
+                self.step()
+            self.stream.synchronize()
+            return self.history[: len(prompt) + max_new_tokens].cpu().tolist()
+        for t in prompt[1:]:  # teacher-forced, one decode step per prompt token
             self.step()
             with torch.cuda.stream(self.stream):
                 self.token.fill_(t)

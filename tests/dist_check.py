@@ -136,6 +136,24 @@ def main():
             dist.all_gather_object(toks_all, toks_tp)
             assert all(t == toks_all[0] for t in toks_all), "ranks generated different tokens"
             log(f"TP decode ({engine} engine) vs single GPU: worst logit err", worst, "tokens", toks_tp[:8])
+            # ---- batched prompt prefill under TP (Linears on the fused tensor-core kernel, K-sharded ones all-reduced) vs one GPU,
+            #      then a decode step on top of the prefilled KV caches
+            prompt = [1, 9, 77, 5, 300, 2, 11, 45, 600, 3, 8, 90]
+            full.reset(1)
+            tp.reset(1)
+            t_full, t_tp = full.prefill(prompt), tp.prefill(prompt)
+            for phase in ("prefill", "decode after prefill"):
+                a, b = full.logits.float()[rank * vl:(rank + 1) * vl], tp.logits.float()
+                err = float((a - b).abs().max() / full.logits.float().abs().max())
+                assert err <= 1e-2, (engine, phase, err)
+                assert int(tp.token.cpu()[0]) == int(full.token.cpu()[0]) or err_margin(full.logits.float()), (engine, phase)
+                if phase == "prefill":
+                    assert int(tp.pos.cpu()[0]) == len(prompt) and t_tp == int(tp.token.cpu()[0])
+                    for mdl in (full, tp):
+                        mdl.token.fill_(t_full)
+                        mdl.step()
+                        mdl.stream.synchronize()
+            log(f"TP prefill ({engine} engine): logits match the single-GPU prefill, decode continues on the prefilled caches")
             # ---- vocab-sharded temperature / top-k sampling == the single-GPU sampler on the gathered logits, every token
             L = _lib.lib()
             for (temp, k) in ((0.8, 8), (1.3, None), (0.7, 1)):

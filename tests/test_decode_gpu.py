@@ -81,6 +81,46 @@ def test_decode_steps_match_oracle(model, bits, nsplit, engine):
 
 
 @pytest.mark.parametrize("engine", ["persistent", "launches"])
+@pytest.mark.parametrize("model,bits,T", [("tiny128", 2, 40), ("tiny128", 3, 12), ("golden-tiny", 4, 6), ("tiny128", 4, 100)])
+def test_batched_prefill_matches_oracle_and_sequential_decode(model, bits, T, engine):
+    """APTransformer.prefill (whole prompt in one pass, Linears on the fused tcgen05 kernel from 9 tokens on, batched LUT GEMV
+    below) against the oracle stepped over the same prompt, and against the model's own token-by-token path: logits of the
+    last prompt token within TOL, KV caches within fp16 noise, the same continuation where the oracle's margin allows."""
+    from guidedquant_b200.model import ROPE_BASE
+    from oracle.decode_oracle import DecodeOracle
+
+    S = 128
+    m, dense, cfg = _build(model, bits, S, seed=11, engine=engine)
+    o = DecodeOracle(dense, cfg["n_layer"], cfg["n_head"], cfg["n_kv"], cfg["dim"], S, rope_base=ROPE_BASE[model], half_rounding=True)
+    rng = np.random.default_rng(T)
+    prompt = [1] + [int(t) for t in rng.integers(2, cfg["vocab"], T - 1)]
+    for pos, tok in enumerate(prompt):
+        ref = o.step(tok, pos).numpy()
+    m.reset(prompt[0])
+    first = m.prefill(prompt)
+    logits = m.logits.float().cpu().numpy()
+    err = np.abs(logits - ref).max() / np.abs(ref).max()
+    assert err <= TOL, (model, bits, T, err)
+    assert int(m.pos.cpu()[0]) == T and m.history[:T].cpu().tolist() == prompt and first == int(np.argmax(logits))
+    kc = torch.stack([c[:, :T] for c in m.k_cache]).float().cpu()
+    vc = torch.stack([c[:, :T] for c in m.v_cache]).float().cpu()
+    # the same prompt one decode step per token: caches and continuation
+    cont_prefill = m.generate(prompt, 6)
+    m2, _, _ = _build(model, bits, S, seed=11, engine=engine)
+    cont_seq = m2.generate(prompt, 6, prefill=False)
+    kc2 = torch.stack([c[:, :T] for c in m2.k_cache]).float().cpu()
+    vc2 = torch.stack([c[:, :T] for c in m2.v_cache]).float().cpu()
+    assert float((kc - kc2).abs().max()) <= 2e-2 * float(kc2.abs().max())
+    assert float((vc - vc2).abs().max()) <= 2e-2 * float(vc2.abs().max())
+    assert cont_prefill[:T] == prompt and len(cont_prefill) == T + 6
+    top2 = np.sort(ref)[-2:]
+    if top2[1] - top2[0] > 2 * TOL * np.abs(ref).max():
+        assert cont_prefill[T] == cont_seq[T] == int(np.argmax(ref))
+    if m.prog is not None:
+        m.prog.check()
+
+
+@pytest.mark.parametrize("engine", ["persistent", "launches"])
 def test_generate_is_deterministic_and_graph_equals_eager(engine):
     m, dense, cfg = _build("tiny128", 2, 64, seed=5, engine=engine)
     a = m.generate([1], 20)
