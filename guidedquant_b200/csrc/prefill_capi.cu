@@ -78,17 +78,17 @@ int make_plan(uint32_t T, uint32_t N, uint32_t K, int bits, int sms, int allow_s
     return APG_OK;
 }
 
-template <int BITS>
+template <int BITS, int MINB>
 int launch(const CUtensorMap &map, const Params &p, const Plan &pl, cudaStream_t stream) {
     static bool attr_set[64] = {};
     int dev = 0;
     PTC_CUDA(cudaGetDevice(&dev));
     if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-        PTC_CUDA(cudaFuncSetAttribute(prefill_tc_kernel<BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM_LIMIT - 1024u)));
+        PTC_CUDA(cudaFuncSetAttribute(prefill_tc_kernel<BITS, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM_LIMIT - 1024u)));
         attr_set[dev] = true;
     }
     const dim3 grid(pl.row_tiles, pl.tok_tiles, pl.splits);
-    prefill_tc_kernel<BITS><<<grid, THREADS, pl.smem_bytes, stream>>>(map, p);
+    prefill_tc_kernel<BITS, MINB><<<grid, THREADS, pl.smem_bytes, stream>>>(map, p);
     PTC_CUDA(cudaGetLastError());
     return APG_OK;
 }
@@ -144,10 +144,13 @@ int apg_prefill_gemm(const void *x, void *out, const void *qweight, const void *
     p.t_tile = pl.t_tile, p.stages = pl.stages, p.splits = pl.splits, p.sb_total = pl.sb_total, p.tmem_cols = pl.tmem_cols;
     // instruction descriptor (kind::f16): D fp32, A/B fp16, both K-major, N = t_tile, M = 128
     p.idesc = (1u << 4) | ((pl.t_tile >> 3) << 17) | ((uint32_t)(ROWS >> 4) << 24);
+    // small token tiles on a grid of more CTAs than SMs: the 96-register build, two CTAs per SM (measured: 28672x4096 3-bit,
+    // 16 tokens 63 -> 38 us; on grids that give every SM one CTA anyway the tighter register budget only costs)
+    const bool two = pl.t_tile <= 128u && (uint64_t)pl.row_tiles * pl.tok_tiles * pl.splits > (uint64_t)sms;
     switch (bits) {
-        case 2: st = launch<2>(map, p, pl, stream); break;
-        case 3: st = launch<3>(map, p, pl, stream); break;
-        default: st = launch<4>(map, p, pl, stream); break;
+        case 2: st = two ? launch<2, 2>(map, p, pl, stream) : launch<2, 1>(map, p, pl, stream); break;
+        case 3: st = two ? launch<3, 2>(map, p, pl, stream) : launch<3, 1>(map, p, pl, stream); break;
+        default: st = launch<4, 1>(map, p, pl, stream); break;
     }
     if (st != APG_OK) return st;
     if (pl.splits > 1) {

@@ -291,8 +291,10 @@ struct Net<4> {
 };
 
 // ------------------------------------------------------------------------------------------------ kernel
-template <int BITS>
-__global__ void __launch_bounds__(THREADS, 1) prefill_tc_kernel(const __grid_constant__ CUtensorMap map_x, const Params p) {
+// MINB = CTAs per SM the register allocation must allow: 2 for token tiles <= 128 (bits 2 / 3), where a CTA is a latency chain
+// (lookup -> tcgen05.st -> wait::st per 64 k, IPC 0.14 per warp) and a second resident CTA fills the gaps; 1 otherwise
+template <int BITS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) prefill_tc_kernel(const __grid_constant__ CUtensorMap map_x, const Params p) {
     extern __shared__ __align__(16) uint8_t ptc_smem[];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t s0 = smem_u32(ptc_smem);
