@@ -222,6 +222,44 @@ def graph_time(torch, fn, stream, steps, warm):
     return e0.elapsed_time(e1) * 1e-3 / steps
 
 
+def prefill_probe(torch, model, bits):
+    """the prompt-prefill branch of a Linear, outside the timed region: fused dequant + tcgen05 GEMM kernel
+    (apg_prefill_gemm) vs the reference's route (anyprec_dequant + library fp16 matmul, APLinear.py:35-38) on the model's
+    w1w3 shape, each captured in a CUDA graph over rotating weight copies (> L2), plus the measured error vs fp64"""
+    from guidedquant_b200 import ap_gemv
+    from guidedquant_b200.runtime import MODEL_CONFIGS, linear_shapes
+
+    N, K = linear_shapes(MODEL_CONFIGS[model])["w1w3"]
+    g = torch.Generator(device="cuda").manual_seed(7)
+    ncopy = 4
+    qs = [torch.randint(-2**31, 2**31 - 1, (bits, N, K // 32), dtype=torch.int32, device="cuda", generator=g) for _ in range(ncopy)]
+    lut = (torch.randn((N, 1 << bits), device="cuda", generator=g) * 0.02).half()
+    out = {"linear": f"w1w3 {N}x{K}", "bits": bits, "what": "us per Linear call, CUDA graph of 4 calls over distinct weight copies",
+           "kernel": "apg::ptc::prefill_tc_kernel (tcgen05.mma, A operand dequantised into TMEM, token tiles by TMA)", "tokens": {}}
+    st = torch.cuda.Stream()
+    for T in (64, 512):
+        x = torch.randn((T, K), device="cuda", generator=g).half()
+
+        def fused():
+            for q in qs:
+                ap_gemv.anyprec_prefill_gemm(x, q, lut, bits)
+
+        def ref():
+            for q in qs:
+                torch.matmul(x, ap_gemv.anyprec_dequant(q, lut, bits).T)
+
+        W = ap_gemv.anyprec_dequant(qs[0], lut, bits)
+        y = ap_gemv.anyprec_prefill_gemm(x, qs[0], lut, bits)
+        truth = x.double() @ W.double().T
+        err = float((y.double() - truth).abs().max() / truth.abs().max())
+        del W, truth
+        t_f = graph_time(torch, fused, st, 10, 2) / ncopy
+        t_r = graph_time(torch, ref, st, 10, 2) / ncopy
+        out["tokens"][str(T)] = {"fused_us": t_f * 1e6, "dequant_matmul_us": t_r * 1e6, "speedup": t_r / t_f,
+                                 "fused_TFLOPs": 2.0 * T * N * K / t_f / 1e12, "err_vs_f64": err}
+    return out
+
+
 def parity_probe(torch, model, bits):
     """measured max error of the default GEMV path at the model's four Linear shapes vs the reference kernel and fp64"""
     from guidedquant_b200 import ap_gemv
@@ -531,6 +569,11 @@ def main():
                                 "frac_of_peak_all_bytes": bt["total"] / t_step / 1e9 / peak}
     if parity is not None:
         line["parity"] = parity
+    if want_extra and world == 1:
+        try:
+            line["prefill_tc"] = prefill_probe(torch, model, a.bits)
+        except Exception as e:
+            line["prefill_tc"] = {"failed": repr(e)[:300]}
     for k in ("ref_kernel_baseline", "plugin_path"):
         if k in ch:
             line[k] = ch[k]
