@@ -61,7 +61,7 @@ __device__ __forceinline__ void rope4(const __half (&v)[4], const __half (&partn
 //   3. P.V: lane = (step mod 4, 16-dim group); 4 steps per instruction, 4x unrolled
 // The warps' (m, l, acc[128]) meet in shared memory; warp 0 merges them, adds the current step (whose k, v are still in
 // registers: the cache row written by this launch is never read by it) and writes the head's output or split partial.
-constexpr int kAttnWarps = 4;
+constexpr int kAttnWarps = 8;
 
 __global__ void __launch_bounds__(32 * kAttnWarps) attn_decode_kernel(
     const __half *__restrict__ qkv, const float *__restrict__ inv_freq, __half *__restrict__ k_cache,
