@@ -5,7 +5,7 @@
 //
 //     Y[t, n] = sum_k X[t, k] * lut[n, idx[n, k]]            X fp16 [T, K], Y fp16 [T, N], fp32 accumulation
 //
-// Machine mapping (one CTA = 128 weight rows x T_TILE tokens x a range of K; DESIGN.md §9):
+// Machine mapping (one CTA = 128 weight rows x T_TILE tokens x a range of K; DESIGN.md §11):
 //   * "swap-AB": the 128 weight rows are the M side of tcgen05.mma (cta_group::1, kind::f16, M = 128), the tokens are the
 //     N side (N = T_TILE, 32..256), so a decode-sized token tile still uses the full 128-lane datapath.  The fp32
 //     accumulator tile [128 lanes x T_TILE columns] lives in TMEM.
