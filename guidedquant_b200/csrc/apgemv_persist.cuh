@@ -92,7 +92,8 @@ struct PkShared {
     PJob jobs[2];               // the consumers' current job (slot j & 1) and the next one, copied from global memory
     uint32_t *err;
     uint32_t tag_base;          // epoch * n_jobs
-    uint32_t q_base;            // stage sequence number of the current job's first stage (this CTA)
+    uint32_t q_base[2];         // stage sequence number of the first stage of job j (this CTA) in slot j & 1: the slot of the
+                                // NEXT job is written while the current one runs, so no barrier separates update and use
     long long *prof;            // this CTA's 4 clock stamps of the current job (debug), or nullptr
     // cooperative weight producer (pk_produce): cursor over (job, stage), ring allocation state, try-lock
     const PJob *jobs_g;
@@ -317,7 +318,7 @@ __device__ __noinline__ void pk_gemv_job(const uint32_t slot) {
         const uint32_t ring0 = g_sh.ring0;
         const uint32_t row_bytes = K >> 3;
         for (uint32_t s = g; s < nstages; s += G) {
-            const uint32_t q = g_sh.q_base + s, b = q & (PK_NB - 1u), par = (q / PK_NB) & 1u;
+            const uint32_t q = g_sh.q_base[slot] + s, b = q & (PK_NB - 1u), par = (q / PK_NB) & 1u;
             const uint32_t row0 = r_begin + s * RS;
             const uint32_t rows = min(RS, r_end - row0);
             __syncwarp();
@@ -753,7 +754,7 @@ __global__ void __launch_bounds__(PK_THREADS, 1) decode_persistent_kernel(const 
         // to make ptxas serialise every table lookup with its FMA).
         constexpr uint32_t NPC = sizeof(PJob) / 16;  // 16-byte pieces of a descriptor, one per thread
         if (threadIdx.x < NPC) reinterpret_cast<uint4 *>(&g_sh.jobs[0])[threadIdx.x] = __ldg(reinterpret_cast<const uint4 *>(p.jobs) + threadIdx.x);
-        if (threadIdx.x == 0) g_sh.tag_base = ep * p.n_jobs, g_sh.q_base = 0;
+        if (threadIdx.x == 0) g_sh.tag_base = ep * p.n_jobs, g_sh.q_base[0] = 0;
 #pragma unroll 1
         for (uint32_t j = 0; j < p.n_jobs; j++) {
             bar_consumers();  // descriptor j is in its slot; everyone is done with job j-1 (`red`, x staging, scratch, slot (j+1)&1)
@@ -765,17 +766,19 @@ __global__ void __launch_bounds__(PK_THREADS, 1) decode_persistent_kernel(const 
                 if (p.prof) g_sh.prof[0] = clock64();
             }
             const PJob &jb = g_sh.jobs[j & 1u];
-            switch (jb.type) {
-                case PJ_GEMV: {
-                    pk_gemv_job<BITS>(j & 1u);
-                    bar_consumers();  // all warps are past their last use of q_base
-                    if (threadIdx.x == 0) {
-                        uint32_t r_begin, r_end;
-                        pk_rows(jb, r_begin, r_end);
-                        g_sh.q_base += (r_end - r_begin + jb.rs - 1) / jb.rs;
-                    }
-                    break;
+            // stage numbering of the next job, written into the OTHER slot now: its previous readers (job j-1) are behind the
+            // barrier above, its next readers (job j+1) behind the next one — no barrier of its own
+            if (threadIdx.x == 0) {
+                uint32_t nst = 0;
+                if (jb.type == PJ_GEMV) {
+                    uint32_t r_begin, r_end;
+                    pk_rows(jb, r_begin, r_end);
+                    nst = (r_end - r_begin + jb.rs - 1) / jb.rs;
                 }
+                g_sh.q_base[(j + 1) & 1u] = g_sh.q_base[j & 1u] + nst;
+            }
+            switch (jb.type) {
+                case PJ_GEMV: pk_gemv_job<BITS>(j & 1u); break;
                 case PJ_ATTN: pk_attn_job(j & 1u, p.pos); break;
                 case PJ_PACK: pk_pack_job(j & 1u); break;
                 case PJ_REDUCE: pk_reduce_job(j & 1u); break;
