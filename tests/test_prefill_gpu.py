@@ -39,6 +39,7 @@ def _nerr(y, ref):
 CASES = [  # (N, K, T)
     (128, 256, 16), (256, 1024, 9), (200, 512, 33), (512, 4096, 64), (4096, 4096, 200), (1024, 4096, 256),
     (384, 11008, 77), (256, 14336, 300), (6144, 4096, 1100), (1000, 2048, 130),
+    (28672, 4096, 520), (4096, 14336, 2048),   # the benchmarked w1w3 / w2 shapes: 12-waves grids, three token tiles / eight
 ]
 
 
