@@ -77,6 +77,14 @@ __global__ void __launch_bounds__(32 * kAttnWarps) attn_decode_kernel(
     for (int j = 0; j < 4; j++) fr4[j] = inv_freq[(4 * lane + j) & 63];  // static table: before the dependency wait
     apg::pdl_wait_prior_grid();
     apg::pdl_launch_dependents();  // wo's weight stream may start while we attend; it waits for us before reading `out`
+    // the new q / k / v rows and the position are fetched together (one L2 round trip, not two): none of the addresses
+    // depends on the position
+    uint2 qv = make_uint2(0u, 0u), kvn = qv, vvn = qv;
+    if (w == 0) {
+        qv = *reinterpret_cast<const uint2 *>(qkv + (size_t)h * kHeadDim + 4 * lane);
+        kvn = *reinterpret_cast<const uint2 *>(qkv + (size_t)(H + kvh) * kHeadDim + 4 * lane);
+        vvn = *reinterpret_cast<const uint2 *>(qkv + (size_t)(H + Hkv + kvh) * kHeadDim + 4 * lane);
+    }
     const int pos = *pos_ptr;
     if (pos < 0 || pos >= (int)S) return;  // cache full: never write outside it (the host API refuses to get here)
 
@@ -93,13 +101,10 @@ __global__ void __launch_bounds__(32 * kAttnWarps) attn_decode_kernel(
             rc[j] = __float2half_rn(cs), rs[j] = __float2half_rn(sn);
         }
         __half q[4], kn[4], qp[4], kp[4], qr[4];
-        const uint2 qv = *reinterpret_cast<const uint2 *>(qkv + (size_t)h * kHeadDim + 4 * lane);
-        const uint2 kv = *reinterpret_cast<const uint2 *>(qkv + (size_t)(H + kvh) * kHeadDim + 4 * lane);
-        const uint2 vv = *reinterpret_cast<const uint2 *>(qkv + (size_t)(H + Hkv + kvh) * kHeadDim + 4 * lane);
-        *reinterpret_cast<uint2 *>(q) = qv, *reinterpret_cast<uint2 *>(kn) = kv, *reinterpret_cast<uint2 *>(vn) = vv;
+        *reinterpret_cast<uint2 *>(q) = qv, *reinterpret_cast<uint2 *>(kn) = kvn, *reinterpret_cast<uint2 *>(vn) = vvn;
         uint2 qpv, kpv;
         qpv.x = __shfl_xor_sync(0xffffffffu, qv.x, 16), qpv.y = __shfl_xor_sync(0xffffffffu, qv.y, 16);
-        kpv.x = __shfl_xor_sync(0xffffffffu, kv.x, 16), kpv.y = __shfl_xor_sync(0xffffffffu, kv.y, 16);
+        kpv.x = __shfl_xor_sync(0xffffffffu, kvn.x, 16), kpv.y = __shfl_xor_sync(0xffffffffu, kvn.y, 16);
         *reinterpret_cast<uint2 *>(qp) = qpv, *reinterpret_cast<uint2 *>(kp) = kpv;
         rope4(q, qp, lane, rc, rs, qr);
         rope4(kn, kp, lane, rc, rs, kr);
