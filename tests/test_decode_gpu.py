@@ -81,7 +81,8 @@ def test_decode_steps_match_oracle(model, bits, nsplit, engine):
 
 
 @pytest.mark.parametrize("engine", ["persistent", "launches"])
-@pytest.mark.parametrize("model,bits,T", [("tiny128", 2, 40), ("tiny128", 3, 12), ("golden-tiny", 4, 6), ("tiny128", 4, 100)])
+@pytest.mark.parametrize("model,bits,T", [("tiny128", 2, 40), ("tiny128", 3, 12), ("golden-tiny", 4, 6), ("tiny128", 4, 100),
+                                          ("golden-tiny", 2, 600)])   # long context: several attention rounds, split + merge
 def test_batched_prefill_matches_oracle_and_sequential_decode(model, bits, T, engine):
     """APTransformer.prefill (whole prompt in one pass, Linears on the fused tcgen05 kernel from 9 tokens on, batched LUT GEMV
     below) against the oracle stepped over the same prompt, and against the model's own token-by-token path: logits of the
@@ -89,7 +90,7 @@ def test_batched_prefill_matches_oracle_and_sequential_decode(model, bits, T, en
     from guidedquant_b200.model import ROPE_BASE
     from oracle.decode_oracle import DecodeOracle
 
-    S = 128
+    S = 128 if T < 120 else 1024
     m, dense, cfg = _build(model, bits, S, seed=11, engine=engine)
     o = DecodeOracle(dense, cfg["n_layer"], cfg["n_head"], cfg["n_kv"], cfg["dim"], S, rope_base=ROPE_BASE[model], half_rounding=True)
     rng = np.random.default_rng(T)
