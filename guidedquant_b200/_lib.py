@@ -148,7 +148,7 @@ def lib() -> ctypes.CDLL:
     L.apg_gemv_fused_push.argtypes = [vp, vp, vp, u32, u32, i32, vp, ctypes.c_float, i32, u32, u32,
                                       ctypes.POINTER(vp), vp, vp, u32, vp]
     L.apg_allreduce_finish.restype = i32
-    L.apg_allreduce_finish.argtypes = [vp, vp, vp, vp, u32, u32, u32, vp]
+    L.apg_allreduce_finish.argtypes = [vp, vp, vp, vp, vp, u32, u32, u32, vp]
     L.apg_prefetch_hint.restype = i32
     L.apg_prefetch_hint.argtypes = [vp, ctypes.c_uint64]
     L.apg_round_f32_to_f16.restype = i32
@@ -179,7 +179,7 @@ def check(status: int, what: str) -> None:
         raise RuntimeError(f"{what}: {msg}{extra}")
 
 
-APG_VERSION = 201  # include/apgemv_b200.h: major*100 + minor
+APG_VERSION = 202  # include/apgemv_b200.h: major*100 + minor
 APG_FLAG_REF_ORDER = 0x1
 APG_FLAG_GENERIC = 0x2
 APG_FLAG_PDL = 0x4

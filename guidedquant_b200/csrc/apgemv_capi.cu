@@ -321,13 +321,14 @@ int apg_gemv_fused_push(const void *x, const void *qweight, const void *lut, uin
     return gemv_impl(x, nullptr, scratch_f32, qweight, lut, 1, N, K, bits, flags, 0, stream, fu, true);
 }
 
-int apg_allreduce_finish(const void *recv, uint32_t *epoch, const void *residual, void *out, uint32_t n, uint32_t world,
-                         uint32_t flags, void *stream) {
-    if (!recv || !epoch || !out) return APG_ERR_NULL;
-    if (n == 0 || world < 2 || world > 8) return APG_ERR_SHAPE;
+int apg_allreduce_finish(const void *recv, uint32_t *epoch, uint32_t *done_counter, const void *residual, void *out, uint32_t n,
+                         uint32_t world, uint32_t flags, void *stream) {
+    if (!recv || !epoch || !done_counter || !out) return APG_ERR_NULL;
+    if (n == 0 || (n & 1u) || world < 2 || world > 8) return APG_ERR_SHAPE;
+    if (!aligned(recv, 16) || !aligned(out, 4) || (residual && !aligned(residual, 4))) return APG_ERR_ALIGN;
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(1);
-    cfg.blockDim = dim3(1024);
+    cfg.gridDim = dim3((n / 2u + 255u) / 256u);
+    cfg.blockDim = dim3(256);
     cfg.stream = static_cast<cudaStream_t>(stream);
     cudaLaunchAttribute attr[1];
     if (flags & APG_FLAG_PDL) {
@@ -336,7 +337,7 @@ int apg_allreduce_finish(const void *recv, uint32_t *epoch, const void *residual
         cfg.attrs = attr;
         cfg.numAttrs = 1;
     }
-    APG_CUDA(cudaLaunchKernelEx(&cfg, apg::allreduce_finish_kernel, static_cast<const uint2 *>(recv), epoch,
+    APG_CUDA(cudaLaunchKernelEx(&cfg, apg::allreduce_finish_kernel, static_cast<const uint2 *>(recv), epoch, done_counter,
                                 static_cast<const __half *>(residual), static_cast<__half *>(out), n, world));
     return APG_OK;
 }

@@ -33,6 +33,7 @@ class PushAllReduce:
         assert len(self.peer_base) == self.world and self.peer_base[self.rank] == self.buf.data_ptr()
         self.epoch = torch.zeros(n_sites, dtype=torch.int32, device=self.device)     # per-site epoch counters
         self.scratch = torch.zeros(n_max, dtype=torch.float32, device=self.device)
+        self.done = torch.zeros(n_sites, dtype=torch.int32, device=self.device)      # CTA tickets of the finisher kernels
         torch.cuda.synchronize()
         dist.barrier(self.group)
         vp = ctypes.c_void_p
@@ -58,7 +59,7 @@ class PushAllReduce:
     def finish(self, site: int, out, N: int, residual=None, flags: int = 0):
         """poll all ranks' packets of this site, sum in rank order (+ residual), round to fp16 into `out`."""
         st = _lib.lib().apg_allreduce_finish(self.peer_base[self.rank] + site * self.site_bytes,
-                                             self.epoch.data_ptr() + 4 * site,
+                                             self.epoch.data_ptr() + 4 * site, self.done.data_ptr() + 4 * site,
                                              residual.data_ptr() if residual is not None else None, out.data_ptr(), N,
                                              self.world, flags, torch.cuda.current_stream().cuda_stream)
         _lib.check(st, "apg_allreduce_finish")

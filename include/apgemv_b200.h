@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define APG_VERSION 201 /* major*100 + minor */
+#define APG_VERSION 202 /* major*100 + minor */
 
 enum apg_status {
     APG_OK = 0,
@@ -98,9 +98,10 @@ int apg_gemv_fused(const void *x, void *out, float *partial_f32, const void *qwe
  *                          slot `rank` of EVERY peer's receive buffer peer_recv[p] (uint2 [world][N], peer-mapped device
  *                          memory such as torch symmetric memory) over NVLink: data and flag travel together, so there
  *                          are no fences or atomics and the cost is one one-way NVLink latency.
- *   apg_allreduce_finish : one small kernel that polls this rank's `world` x N packets for the epoch, adds the `world`
- *                          values in rank order (deterministic), adds the optional fp16 residual, rounds to fp16, and
- *                          advances *epoch.
+ *   apg_allreduce_finish : one small kernel (one thread per pair of elements) that polls this rank's `world` x N packets for
+ *                          the epoch, adds the `world` values in rank order (deterministic), adds the optional fp16
+ *                          residual, rounds to fp16; its last CTA (ticket in *done_counter, a zeroed device uint32 per
+ *                          site) advances *epoch.  N even.
  * peer_recv is a HOST array of `world` device pointers; `epoch` is a device uint32 (zero-initialised, one per all-reduce
  * site, advanced identically on every rank) so the same CUDA graph can be replayed; scratch_f32 [N] receives the local
  * un-rounded sums.  world in 2..8.  New functionality: the reference has no multi-GPU inference path.
@@ -108,7 +109,7 @@ int apg_gemv_fused(const void *x, void *out, float *partial_f32, const void *qwe
 int apg_gemv_fused_push(const void *x, const void *qweight, const void *lut, uint32_t N, uint32_t K, int bits,
                         const void *norm_w, float norm_eps, int silu_mul, uint32_t world, uint32_t rank,
                         void *const *peer_recv, const void *epoch, float *scratch_f32, uint32_t flags, void *stream);
-int apg_allreduce_finish(const void *recv, uint32_t *epoch, const void *residual, void *out, uint32_t n, uint32_t world,
+int apg_allreduce_finish(const void *recv, uint32_t *epoch, uint32_t *done_counter, const void *residual, void *out, uint32_t n, uint32_t world,
                          uint32_t flags, void *stream);
 
 /*
