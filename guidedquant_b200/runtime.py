@@ -44,9 +44,12 @@ def linear_shapes(cfg: dict) -> dict:
     }
 
 
-# measured on B200 (Llama-3-8B 2-bit, profiles/r2_engines_by_world.txt): per-launch kernels win on 1 GPU (812 vs 619 tok/s), tie on 2
-# (863 vs 856), the persistent token kernel wins from 4 GPUs on (981 vs 895), where the per-GPU Linears are small
-PERSISTENT_MIN_WORLD = 4
+# Default engine by world size.  Measured on B200 (profiles/r2_engines_by_world.txt), Llama-3-8B 2-bit tok/s, launches vs
+# persistent: 1 GPU 800 vs 619; 2 GPUs 997 vs 856; 4 GPUs ~1100 vs 990; 8 GPUs 1174 vs 1017 (Llama-3-70B: 292 vs 223 at 4,
+# 341 vs 283 at 8).  The persistent engine led at 4-8 GPUs only while the all-reduce finisher of the launches engine was a
+# single CTA; since that kernel runs on several CTAs the per-launch engine wins everywhere and the persistent engine is
+# opt-in (engine="persistent").
+PERSISTENT_MIN_WORLD = 1 << 30
 
 
 def persistent_supported(cfg: dict, bits: int, world: int = 1) -> bool:
