@@ -37,9 +37,9 @@ class APTransformer:
                  world_size: int = 1, rank: int = 0, process_group=None, glu_epilogue: bool | None = None,
                  engine: str | None = None):
         self.cfg = dict(MODEL_CONFIGS[model])
-        # "persistent" (default from 4 GPUs on): embedding + all blocks of a token are ONE cooperative launch of
-        # the persistent token kernel (persist.py / csrc/apgemv_persist.cuh), then lm_head + sampling;
-        # "launches" (default on one GPU, measured faster there): one PDL launch per op
+        # "launches" (default, measured fastest at every world size): one PDL launch per op;
+        # "persistent" (opt-in): embedding + all blocks of a token are ONE cooperative launch of the persistent token kernel
+        # (persist.py / csrc/apgemv_persist.cuh), then lm_head + sampling
         self.engine = engine or ("persistent" if world_size >= PERSISTENT_MIN_WORLD and persistent_supported(self.cfg, bits, world_size)
                                  else "launches")
         assert self.engine in ("launches", "persistent"), f"unknown decode engine {engine!r}"
