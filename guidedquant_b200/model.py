@@ -51,14 +51,13 @@ class APTransformer:
         self.model, self.bits, self.S, self.eps = model, bits, max_seq_len, norm_eps
         # w1w3's rows are kept interleaved (gate_i, up_i) so that its epilogue writes silu(gate)*up once per element instead
         # of every CTA of the w2 launch recomputing the activation in its prologue: same roundings -> identical logits,
-        # measured 5 % faster per token on B200 (profiles/r2_ab_glu.log).  Always on in the persistent engine; in the
-        # launches engine it is the single-GPU default (its K-sharded w2 path keeps the prologue form).
+        # measured 5 % faster per token on B200 (profiles/r2_ab_glu.log).  Always on in the persistent engine, the default
+        # of the launches engine (under tensor parallelism every rank interleaves its own gate / up columns).
         if self.engine == "persistent":
             assert glu_epilogue in (None, True), "the persistent engine always uses the SwiGLU epilogue"
             self.glu_epilogue = True
         else:
-            self.glu_epilogue = (world_size == 1) if glu_epilogue is None else bool(glu_epilogue)
-            assert not (self.glu_epilogue and world_size > 1), "glu_epilogue is single-GPU only in the launches engine"
+            self.glu_epilogue = True if glu_epilogue is None else bool(glu_epilogue)
         self.flags = _lib.APG_FLAG_PDL if pdl else 0
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
         self.rope_base = ROPE_BASE.get(model, 10000.0)
@@ -345,9 +344,11 @@ class APTransformer:
                 self.push.gemv_push(2 * i, self.att, sd[p + "attention.wo.qweight"], sd[p + "attention.wo.lut"], no, ko,
                                     self.bits, flags=fl)
                 self.push.finish(2 * i, self.h, no, residual=self.x, flags=fl)
-                self._fused(self.h, self.gu, p + "feed_forward.w1w3", ng, kg, norm=sd[p + "post_attention_layernorm.weight"])
+                glu = self.glu_epilogue
+                self._fused(self.h, self.gu, p + "feed_forward.w1w3", ng, kg, norm=sd[p + "post_attention_layernorm.weight"],
+                            silu_mul=2 if glu else 0)
                 self.push.gemv_push(2 * i + 1, self.gu, sd[p + "feed_forward.w2.qweight"], sd[p + "feed_forward.w2.lut"],
-                                    n2, k2, self.bits, silu_mul=1, eps=self.eps, flags=fl)
+                                    n2, k2, self.bits, silu_mul=0 if glu else 1, eps=self.eps, flags=fl)
                 self.push.finish(2 * i + 1, self.x, n2, residual=self.h, flags=fl)
                 self.launches_per_token += 4
 
