@@ -57,7 +57,14 @@ class APTransformer:
             assert glu_epilogue in (None, True), "the persistent engine always uses the SwiGLU epilogue"
             self.glu_epilogue = True
         else:
-            self.glu_epilogue = True if glu_epilogue is None else bool(glu_epilogue)
+            if glu_epilogue is None:   # the epilogue variant exists for one chunk per warp and 8-row stages (launch_fast)
+                import ctypes
+
+                plan = (ctypes.c_uint32 * 16)()
+                W_ = max(1, world_size)
+                ok = _lib.lib().apg_plan_fast(2 * (c["inter"] // W_), c["dim"], bits, 0, 148, plan) == 0
+                glu_epilogue = ok and plan[0] == 1 and plan[3] == 8 and (2 * (c["inter"] // W_)) % 4 == 0
+            self.glu_epilogue = bool(glu_epilogue)
         self.flags = _lib.APG_FLAG_PDL if pdl else 0
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
         self.rope_base = ROPE_BASE.get(model, 10000.0)
